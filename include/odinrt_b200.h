@@ -1,0 +1,224 @@
+/* odinrt_b200.h — C ABI of libodinrt_b200.so
+ *
+ * Drop-in boundary for the per-pixel path-tracing loop of elteammate/raytracer-odin.
+ * The reference has no FFI seam on this path; the cut is the single call
+ *     render_scene(rc, &scene, number_of_trials)          main.odin:242 -> raytracer.odin:602
+ * Everything before it (glTF load input.odin:13, finish_scene raytracer.odin:62 incl. both
+ * bvh_build calls raytracer.odin:227) and after it (save_result output.odin:82) stays on the host
+ * side (Odin).  The structs below are plain C mirrors of what the Odin side owns at that point;
+ * INTEGRATION.md shows the `foreign import` shim that fills them.
+ *
+ * Conventions: every function returns 0 on success, non-zero on error (ort_last_error() holds
+ * the message; the reference panics on load errors main.odin:195,216 and has no recoverable
+ * render error — the shim panics on non-zero).  The caller owns every host buffer passed in; the
+ * library owns all device memory.  No pointer into caller memory is kept after ort_upload_scene
+ * returns, except `out` / `interrupt` for the duration of a blocking render call.
+ * No C++ exception or torch type crosses this boundary.
+ */
+#ifndef ODINRT_B200_H
+#define ODINRT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORT_ABI_VERSION 1
+
+/* ---- scene data handed over by the host (once per scene) --------------------------------- */
+
+/* Triangle — layout-identical to the Odin `Triangle` (raytracer.odin:18-23), 168 bytes:
+ * p0 u12 v24 n1 36 n2 48 n3 60 ng72 tex1 84 tex2 92 tex3 100 tan1 108 tan2 124 tan3 140
+ * material_index(i64) 160.  Triangles are passed in POST-BUILD order (bvh_build sorts
+ * scene.trigs[1:] in place, raytracer.odin:265-268); the dummy at index 0 (input.odin:43) is NOT
+ * passed, so triangle id == index into this array. */
+typedef struct ort_triangle {
+    float p[3], u[3], v[3];
+    float n1[3], n2[3], n3[3], ng[3];
+    float tex1[2], tex2[2], tex3[2];
+    float tan1[4], tan2[4], tan3[4];
+    int64_t material_index; /* index into ort_scene.materials; Odin's dummy material 0 IS passed */
+} ort_triangle;
+
+/* BVH node — C mirror of the Odin `BVH_Node` (raytracer.odin:211-225): binary, post-order,
+ * root == last element (raytracer.odin:375,380).  kind 0 = leaf: a = first triangle index,
+ * b = triangle count (slice ptr - base)/168, len);  kind 1 = branch: a = left, b = right. */
+typedef struct ort_bvh_node {
+    float lo[3], hi[3];
+    int32_t kind;
+    int32_t _pad;
+    int64_t a, b;
+} ort_bvh_node;
+
+/* Texture — mirror of `Texture` (textures.odin:14-19).  data is u8 or f32 (stb native channel
+ * count, 1..4); stride = elements per row (channels * width, textures.odin:65). */
+typedef struct ort_texture {
+    const void* data;
+    int32_t width, height;
+    int32_t channels;
+    int32_t is_f32; /* 0: [^]u8, 1: [^]f32 */
+    int64_t stride;
+} ort_texture;
+
+/* Material — mirror of `Material` (raytracer.odin:34-43).  Samplers become indices into
+ * ort_scene.textures, -1 == nil sampler. */
+typedef struct ort_material {
+    float color_factor[3];
+    int32_t color_texture;
+    float emission_factor[3];
+    int32_t emission_texture;
+    float metallic_factor;
+    float roughness_factor;
+    int32_t metallic_roughness_texture;
+    int32_t normal_texture;
+} ort_material;
+
+/* Cam — mirror of `Cam` (raytracer.odin:45-49). basis is column-major: basis[3*c + r] is row r
+ * of column c (Odin matrix[3,3]f32; input.odin:105-107).  fov_x already carries the aspect
+ * multiplication of main.odin:202-203. */
+typedef struct ort_camera {
+    float pos[3];
+    float basis[9];
+    float fov_x;
+} ort_camera;
+
+/* Scene — mirror of `Scene` (raytracer.odin:51-60) after finish_scene (raytracer.odin:62-91). */
+typedef struct ort_scene {
+    ort_camera cam;
+    const ort_triangle* triangles;      /* scene.trigs[1:], post-build order */
+    int64_t n_triangles;
+    const ort_bvh_node* bvh;            /* scene.bvh */
+    int64_t n_bvh_nodes;
+    const ort_triangle* light_triangles; /* scene.light_surfaces, post-build order (raytracer.odin:75) */
+    int64_t n_light_triangles;
+    const ort_bvh_node* light_bvh;      /* scene.light_bvh */
+    int64_t n_light_bvh_nodes;
+    const ort_material* materials;      /* scene.materials incl. dummy 0 (input.odin:44) */
+    int64_t n_materials;
+    const ort_texture* textures;        /* de-duplicated textures (input.odin:250-256) */
+    int64_t n_textures;
+    const ort_texture* env_map;         /* scene.env_map (main.odin:213-220) or NULL */
+} ort_scene;
+
+/* ---- render output ------------------------------------------------------------------------ */
+
+/* Sample_Stats — layout-identical to main.odin:34-40, 52 bytes.  Pixel (x,y) lives at index
+ * (H-1-y)*W + x (rc_set_pixel, main.odin:95). */
+typedef struct ort_sample_stats {
+    float first[3];
+    uint32_t count;
+    float last[3];
+    float total[3];
+    float total_squared[3];
+} ort_sample_stats;
+
+typedef struct ort_ray {
+    float o[3];
+    float d[3];
+} ort_ray; /* Ray, raytracer.odin:105-107 */
+
+/* Result of cast_ray (raytracer.odin:416-430).  tri == -1 is the reference's `trig == nil`. */
+typedef struct ort_hit {
+    float t;    /* includes the + RAY_EPS of raytracer.odin:428 */
+    float u, v; /* hit.uv */
+    int32_t tri;      /* index into ort_scene.triangles, -1 on miss */
+    int32_t material; /* triangles[tri].material_index ("primitive id"), -1 on miss */
+    int32_t inside;   /* hit.inside */
+} ort_hit;
+
+typedef struct ort_device_cfg {
+    int32_t device;     /* CUDA device ordinal */
+    int32_t _pad;
+    uint64_t seed;      /* key of the counter-based per-pixel RNG streams */
+    int64_t max_paths_in_flight; /* 0 = default; path-state capacity of one wave */
+} ort_device_cfg;
+
+typedef struct ort_stats {
+    uint64_t rays_closest;   /* cast_ray calls (raytracer.odin:435): primary + continuation */
+    uint64_t rays_light_pdf; /* surface_sampling_pdf traversals (shading.odin:98) */
+    uint64_t paths;          /* pixel-samples completed */
+    uint64_t kernel_launches;/* launches of this library's own kernels */
+    double   render_ms;      /* device time of the last render call (CUDA events) */
+    double   trace_ms;       /* device time spent in closest-hit trace kernels, last profiled call */
+    double   light_ms;
+    double   shade_ms;
+    double   other_ms;
+    /* wide-BVH facts fixed at upload time */
+    int64_t  wide_nodes, wide_depth, light_wide_nodes;
+    int64_t  device_bytes;
+} ort_stats;
+
+typedef struct ort_ctx ort_ctx;
+
+/* ---- entry points ------------------------------------------------------------------------- */
+
+int  ort_abi_version(void);
+
+/* Create / destroy one rendering context bound to one GPU.  Fails (non-zero) when no sm_100
+ * class device is present: there is no CPU fallback. */
+int  ort_create(ort_ctx** out, const ort_device_cfg* cfg);
+void ort_destroy(ort_ctx* ctx);
+const char* ort_last_error(const ort_ctx* ctx); /* ctx may be NULL: last error of ort_create */
+
+/* Run all subsequent work of this context on an externally owned cudaStream_t (e.g. torch's
+ * current stream). NULL = the context's own stream. */
+int  ort_set_stream(ort_ctx* ctx, void* cuda_stream);
+
+/* Deep-copies the scene to the device: re-emits the reference BVHs (scene + light) as flattened
+ * wide-node layouts, builds traversal/shading triangle records, material table and texture
+ * objects.  Replaces: the scene hand-off into render_scene (raytracer.odin:602). */
+int  ort_upload_scene(ort_ctx* ctx, const ort_scene* scene);
+
+/* Blocking render of samples [first_sample, first_sample + n_samples) for every pixel of a
+ * w x h image, accumulated INTO `out` (w*h ort_sample_stats, host memory), like render_scene
+ * accumulates into rc.pixels[0] across --times trials without clearing (raytracer.odin:606-610).
+ * `interrupt` (may be NULL) is polled between waves like is_interrupted() (raytracer.odin:554);
+ * on interrupt the samples finished so far are written and 0 is returned.
+ * Replaces: render_scene / render_task / raytrace / rc_set_pixel
+ * (raytracer.odin:602,528,432; main.odin:89). */
+int  ort_render(ort_ctx* ctx, uint32_t w, uint32_t h, int32_t ray_depth,
+                uint64_t first_sample, uint64_t n_samples,
+                ort_sample_stats* out, const volatile uint8_t* interrupt);
+
+/* Same render, device-resident: accumulates into a caller-owned DEVICE buffer of 8*w*h floats,
+ * planar: total.r,g,b | total_squared.r,g,b | count (as float) | reserved, each plane w*h in
+ * ort_sample_stats pixel order ((H-1-y)*W+x).  Asynchronous on the context stream.  This is the
+ * buffer multi-GPU hosts reduce (one NCCL reduce per frame) before unpacking. */
+int  ort_render_device(ort_ctx* ctx, uint32_t w, uint32_t h, int32_t ray_depth,
+                       uint64_t first_sample, uint64_t n_samples, float* d_accum);
+
+/* Unpack a planar device accumulator into host Sample_Stats (adds to `out`). */
+int  ort_unpack_accum(ort_ctx* ctx, uint32_t w, uint32_t h, const float* d_accum,
+                      ort_sample_stats* out);
+
+/* Parity probes.  ort_trace_rays == cast_ray (raytracer.odin:416) on n host rays;
+ * ort_primary_hits generates the primary ray of `sample` for every pixel exactly as render does
+ * (render_task, raytracer.odin:580-593) and returns its cast_ray result, pixel order y*w + x
+ * (unflipped). */
+int  ort_trace_rays(ort_ctx* ctx, const ort_ray* rays, int64_t n, ort_hit* out);
+int  ort_primary_hits(ort_ctx* ctx, uint32_t w, uint32_t h, uint64_t sample, ort_hit* out,
+                      ort_ray* rays_out /* may be NULL */);
+/* Sum of surface_sampling_pdf_bvh_sum (shading.odin:62-94) / n_lights for n host rays. */
+int  ort_light_pdf(ort_ctx* ctx, const ort_ray* rays, int64_t n, float* out);
+
+/* Tone-map on device: get_rgb_image (output.odin:30-80, mode Mean) from a planar device
+ * accumulator to w*h*3 bytes (host). SURVEY §8(f) rank 2. */
+int  ort_tonemap_rgb8(ort_ctx* ctx, uint32_t w, uint32_t h, const float* d_accum, uint8_t* out_rgb);
+
+int  ort_get_stats(ort_ctx* ctx, ort_stats* out);
+int  ort_reset_stats(ort_ctx* ctx);
+/* When on, render calls time each kernel class with CUDA events (serialises the pipeline). */
+int  ort_set_profiling(ort_ctx* ctx, int32_t on);
+
+/* Host-side scene finalisation helper (NOT used when Odin is the host): the reference
+ * bvh_build (raytracer.odin:227-342) as native code, for hosts that do not have one.
+ * Sorts `tris` in place like the reference; writes up to `cap` nodes, returns node count
+ * (or a negative error code). */
+int64_t ort_bvh_build(ort_triangle* tris, int64_t n, ort_bvh_node* nodes_out, int64_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ODINRT_B200_H */

@@ -1,0 +1,168 @@
+"""`Renderer`: the call sequence the Odin shim makes through `foreign import`,
+expressed in Python over the same C ABI.  Mirrors the reference's hot-path interface:
+
+    finish_scene(rc, &scene)            -> Scene.finish(native_bvh_build)        raytracer.odin:62
+    render_scene(rc, &scene, trials)    -> Renderer.render_scene(...)            raytracer.odin:602
+    rc.pixels[0]                        -> numpy array of Sample_Stats           main.odin:34-40
+
+No CPU fallback: constructing a Renderer without the CUDA library or without a B200-class GPU
+raises RuntimeError.
+"""
+import ctypes as C
+import statistics
+import time
+from typing import Optional
+
+import numpy as np
+
+from . import cabi
+from .scene import Scene
+
+
+class OrtError(RuntimeError):
+    pass
+
+
+class Renderer:
+    def __init__(self, device: int = 0, seed: int = 0, max_paths_in_flight: int = 0):
+        self.lib = cabi.load_library()
+        self._ctx = C.c_void_p()
+        cfg = cabi.OrtDeviceCfg(device=device, seed=seed, max_paths_in_flight=max_paths_in_flight)
+        if self.lib.ort_create(C.byref(self._ctx), C.byref(cfg)) != 0:
+            raise OrtError(self.lib.ort_last_error(None).decode())
+        self.device = device
+        self.scene: Optional[Scene] = None
+
+    # -- lifetime ------------------------------------------------------------------------------
+    def close(self):
+        if self._ctx:
+            self.lib.ort_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise OrtError(self.lib.ort_last_error(self._ctx).decode())
+
+    # -- scene ---------------------------------------------------------------------------------
+    def upload_scene(self, scene: Scene):
+        cs, keep = scene.to_c()
+        self._check(self.lib.ort_upload_scene(self._ctx, C.byref(cs)))
+        del keep  # the library deep-copies; nothing of ours is retained
+        self.scene = scene
+        return self
+
+    def set_stream(self, cuda_stream: int):
+        self._check(self.lib.ort_set_stream(self._ctx, C.c_void_p(cuda_stream)))
+
+    def set_profiling(self, on: bool):
+        self._check(self.lib.ort_set_profiling(self._ctx, 1 if on else 0))
+
+    # -- rendering -----------------------------------------------------------------------------
+    def render(self, width: int, height: int, ray_depth: int, n_samples: int, first_sample: int = 0,
+               out: Optional[np.ndarray] = None, interrupt: Optional[np.ndarray] = None) -> np.ndarray:
+        """One blocking trial into `out` (Sample_Stats[h*w], accumulated like rc.pixels[0])."""
+        if out is None:
+            out = np.zeros(width * height, cabi.STATS_DTYPE)
+        assert out.dtype == cabi.STATS_DTYPE and out.size == width * height and out.flags.c_contiguous
+        iptr = interrupt.ctypes.data_as(C.c_void_p) if interrupt is not None else None
+        self._check(self.lib.ort_render(self._ctx, width, height, ray_depth, first_sample, n_samples,
+                                        cabi.ptr(out), iptr))
+        return out
+
+    def render_scene(self, width, height, ray_depth, n_samples, number_of_trials=1, out=None, log=print):
+        """render_scene (raytracer.odin:602-665): trials accumulate into the same pixels without
+        clearing and replay the same sample indices (:606-610); prints the reference's summary."""
+        if out is None:
+            out = np.zeros(width * height, cabi.STATS_DTYPE)
+        timings = []
+        for trial in range(number_of_trials):
+            t0 = time.perf_counter()
+            self.render(width, height, ray_depth, n_samples, 0, out)
+            dt = time.perf_counter() - t0
+            timings.append(dt)
+            if log:
+                log(f"Trial {trial} >>> Rendered in {dt * 1e3:.3f}ms")
+        if number_of_trials > 1 and log:
+            ts = sorted(timings)
+            mean = statistics.fmean(ts)
+            sd = statistics.stdev(ts)
+            med = (ts[len(ts) // 2] + ts[(len(ts) + 1) // 2 if (len(ts) + 1) // 2 < len(ts) else -1]) / 2
+            log(">>>>>>>>> Performance Summary <<<<<<<<<")
+            log(f"Trials: {number_of_trials}")
+            log(f"Time: {mean * 1e3:.02f}±{sd * 1e3:.02f}ms")
+            log(f"Best: {ts[0] * 1e3:.02f}ms, Median: {med * 1e3:.02f}ms, Worst: {ts[-1] * 1e3:.02f}ms")
+            log(">>>>>>>>> Performance Summary <<<<<<<<<")
+        return out, timings
+
+    def render_device(self, width, height, ray_depth, first_sample, n_samples, d_accum_ptr: int):
+        """Asynchronous render into a device accumulator (8 planes x h*w floats)."""
+        self._check(self.lib.ort_render_device(self._ctx, width, height, ray_depth, first_sample, n_samples,
+                                               C.c_void_p(d_accum_ptr)))
+
+    def unpack_accum(self, width, height, d_accum_ptr: int, out: Optional[np.ndarray] = None) -> np.ndarray:
+        if out is None:
+            out = np.zeros(width * height, cabi.STATS_DTYPE)
+        self._check(self.lib.ort_unpack_accum(self._ctx, width, height, C.c_void_p(d_accum_ptr), cabi.ptr(out)))
+        return out
+
+    def tonemap_rgb8(self, width, height, d_accum_ptr: int) -> np.ndarray:
+        out = np.zeros((height, width, 3), np.uint8)
+        self._check(self.lib.ort_tonemap_rgb8(self._ctx, width, height, C.c_void_p(d_accum_ptr), cabi.ptr(out)))
+        return out
+
+    # -- parity probes -------------------------------------------------------------------------
+    def trace_rays(self, rays: np.ndarray) -> np.ndarray:
+        rays = np.ascontiguousarray(rays, cabi.RAY_DTYPE)
+        out = np.zeros(len(rays), cabi.HIT_DTYPE)
+        self._check(self.lib.ort_trace_rays(self._ctx, cabi.ptr(rays), len(rays), cabi.ptr(out)))
+        return out
+
+    def light_pdf(self, rays: np.ndarray) -> np.ndarray:
+        rays = np.ascontiguousarray(rays, cabi.RAY_DTYPE)
+        out = np.zeros(len(rays), np.float32)
+        self._check(self.lib.ort_light_pdf(self._ctx, cabi.ptr(rays), len(rays), cabi.ptr(out)))
+        return out
+
+    def primary_hits(self, width, height, sample=0, want_rays=False):
+        out = np.zeros(width * height, cabi.HIT_DTYPE)
+        rays = np.zeros(width * height, cabi.RAY_DTYPE) if want_rays else None
+        self._check(self.lib.ort_primary_hits(self._ctx, width, height, sample, cabi.ptr(out),
+                                              cabi.ptr(rays) if want_rays else None))
+        return (out, rays) if want_rays else out
+
+    # -- stats ---------------------------------------------------------------------------------
+    def stats(self) -> dict:
+        s = cabi.OrtStats()
+        self._check(self.lib.ort_get_stats(self._ctx, C.byref(s)))
+        return s.as_dict()
+
+    def reset_stats(self):
+        self._check(self.lib.ort_reset_stats(self._ctx))
+
+
+def mean_image(stats: np.ndarray, width: int, height: int) -> np.ndarray:
+    """Linear mean radiance (total / count), image row order (row 0 = top)."""
+    cnt = np.maximum(stats["count"].astype(np.float32), 1)[:, None]
+    return (stats["total"] / cnt).reshape(height, width, 3)
+
+
+def rel_rmse(a: np.ndarray, b: np.ndarray):
+    """relRMSE = sqrt(mean((a-b)^2)) / mean(b) over RGB, and mean-luminance ratio (Rec.709)."""
+    a = a.astype(np.float64)
+    b = b.astype(np.float64)
+    rmse = float(np.sqrt(np.mean((a - b) ** 2)) / max(np.mean(b), 1e-30))
+    lw = np.array([0.2126, 0.7152, 0.0722])
+    lum = float((a @ lw).mean() / max((b @ lw).mean(), 1e-30))
+    return rmse, lum

@@ -1,0 +1,772 @@
+// kernels.cuh — the wavefront path-tracing kernels (sm_100a).
+//
+//   k_raygen      render_task's inner loop head (raytracer.odin:580-586): jittered pinhole rays
+//   k_trace       cast_ray (raytracer.odin:416-430) on the 4-wide re-emission of the reference
+//                 BVH: persistent warps, shared-memory traversal stack, 16-byte node/triangle loads
+//   k_light       surface_sampling_pdf_bvh_sum (shading.odin:62-94): all-hit sum over the light BVH
+//   k_shade       raytrace's body (raytracer.odin:437-500) + sample/pdf/shade (shading.odin),
+//                 texture fetches through texture objects, ballot/prefix-sum queue compaction
+//   k_resolve     rc_set_pixel (main.odin:89-102): per-pixel accumulation in sample order
+//   k_stats, k_pack_rays, k_unpack_hits, k_pack_stats, k_tonemap: small helpers
+#pragma once
+#include "device_math.cuh"
+#include "wide_bvh.h"
+
+namespace ort {
+
+constexpr float RAY_EPS = 1e-3f; // raytracer.odin:418, shading.odin:66
+constexpr float PI_F = 3.14159265358979323846264338327950288f;
+constexpr float TAU_F = 6.28318530717958647692528676655900576f;
+
+constexpr int TRACE_THREADS = 128;
+constexpr int SMEM_STACK = 12;   // stack entries per thread kept in shared memory
+constexpr int LOCAL_STACK = 116; // overflow entries per thread in local memory
+constexpr int MAX_STACK = SMEM_STACK + LOCAL_STACK;
+
+struct DevMaterial {
+    float color[3], roughness;
+    float emission[3], metallic;
+    int32_t color_tex, emission_tex, mr_tex, normal_tex;
+};
+struct DevTexture {
+    cudaTextureObject_t raw;    // texels as the reference's texture_index returns them, srgb = false
+    cudaTextureObject_t linear; // same with pow(rgb, 2.2) applied per texel (srgb = true), 0 if unused
+    int32_t w, h;
+    int32_t pad0, pad1;
+};
+
+struct SceneDev {
+    const float4* nodes;  // WideNode[], 8 float4 each
+    const float4* tris;   // TriIsect[], 3 float4 each
+    const float4* lnodes; // light BVH
+    const float4* ltris;  // light TriIsect[]
+    const float4* llight; // TriLight[]
+    const float4* tshade; // TriShade[], 4 float4 each
+    const float4* tuv;    // TriUV[], 2 float4 each
+    const float4* ttan;   // TriTan[], 3 float4 each
+    const DevMaterial* mats;
+    const DevTexture* texs;
+    DevTexture env;
+    int32_t has_env;
+    int32_t n_lights;
+    float pad_scale[3];  // max |coordinate| of the scene root box
+    float lpad_scale[3]; // same for the light BVH
+};
+
+struct RenderParams {
+    float M[12]; // rows 0..2 of pixel_to_ray_dir (raytracer.odin:534-538)
+    float cam_pos[3];
+    uint32_t w, h, npix;
+    int32_t ray_depth;
+    uint32_t n_batch_samples;
+    uint64_t sample_base;
+    uint64_t seed;
+};
+
+// ------------------------------------------------------------------------------------------------
+// ray setup shared by both traversal kernels
+// ------------------------------------------------------------------------------------------------
+struct RaySetup {
+    float ox, oy, oz; // origin AFTER the RAY_EPS offset (raytracer.odin:421)
+    float dx, dy, dz;
+    float ix, iy, iz;       // 1/d
+    float nx, ny, nz;       // -o/d - pad   (added to near-plane products)
+    float fx, fy, fz;       // -o/d + pad   (added to far-plane products)
+    int sx, sy, sz;         // float4 index of the near plane inside a node (0/1, 2/3, 4/5)
+};
+
+// Box tests here are CONSERVATIVE with respect to the reference's check_intersect_ray_aabb
+// (raytracer.odin:119-134): that test translates the ray by box.lo and divides, so its slab
+// distances carry an absolute error of a few ulp of (|o| + |box|) / |d|.  Each slab distance is
+// widened by `pad` = 16 ulp of that magnitude so every box the reference enters is entered here
+// too; a superset of boxes cannot change the closest hit, only the triangle test decides.
+__device__ __forceinline__ RaySetup make_ray(float4 o4, float4 d4, const float* pad_scale) {
+    RaySetup r;
+    r.dx = d4.x; r.dy = d4.y; r.dz = d4.z;
+    r.ox = addr(o4.x, mulr(d4.x, RAY_EPS));
+    r.oy = addr(o4.y, mulr(d4.y, RAY_EPS));
+    r.oz = addr(o4.z, mulr(d4.z, RAY_EPS));
+    r.ix = 1.0f / r.dx; r.iy = 1.0f / r.dy; r.iz = 1.0f / r.dz;
+    const float ulp16 = 16.0f * 5.9604645e-08f;
+    float px = ulp16 * (fabsf(r.ox) + pad_scale[0]) * fabsf(r.ix);
+    float py = ulp16 * (fabsf(r.oy) + pad_scale[1]) * fabsf(r.iy);
+    float pz = ulp16 * (fabsf(r.oz) + pad_scale[2]) * fabsf(r.iz);
+    float bx = -r.ox * r.ix, by = -r.oy * r.iy, bz = -r.oz * r.iz;
+    r.nx = bx - px; r.fx = bx + px;
+    r.ny = by - py; r.fy = by + py;
+    r.nz = bz - pz; r.fz = bz + pz;
+    r.sx = r.dx < 0.0f ? 1 : 0;
+    r.sy = r.dy < 0.0f ? 3 : 2;
+    r.sz = r.dz < 0.0f ? 5 : 4;
+    return r;
+}
+
+// intersect_ray_triangle (raytracer.odin:136-150): solve [u | v | -d] (u,v,t)^T = o - p through
+// adjugate * (1/det), every operation individually rounded, sums left to right.  Returns false
+// when the reference would return t = -1.  `c` is the precomputed third adjugate row.
+struct TriHit {
+    float t, u, v;
+};
+__device__ __forceinline__ void tri_det_t(const RaySetup& r, float4 a, float4 b, float4 c, float& id, float& bx,
+                                          float& by, float& bz, float& t, float& a00, float& a10) {
+    // a = (p.x p.y p.z u.x)  b = (u.y u.z v.x v.y)  c = (v.z c0 c1 c2)
+    const float m00 = a.w, m10 = b.x, m20 = b.y;
+    const float m01 = b.z, m11 = b.w, m21 = c.x;
+    const float m02 = -r.dx, m12 = -r.dy, m22 = -r.dz;
+    (void)m00; (void)m20; (void)m01;
+    a00 = subr(mulr(m11, m22), mulr(m21, m12));
+    a10 = -subr(mulr(m10, m22), mulr(m20, m12));
+    const float a20 = c.y;
+    // det = m00*(m11*m22 - m12*m21) + (-m01)*(m10*m22 - m12*m20) + m02*(m10*m21 - m11*m20)
+    //     = m00*a00 + m01*a10 + m02*a20   (same products, same roundings, same order)
+    const float det = addr(addr(mulr(m00, a00), mulr(m01, a10)), mulr(m02, a20));
+    id = divr(1.0f, det);
+    bx = subr(r.ox, a.x); by = subr(r.oy, a.y); bz = subr(r.oz, a.z);
+    t = addr(addr(mulr(mulr(c.y, id), bx), mulr(mulr(c.z, id), by)), mulr(mulr(c.w, id), bz));
+}
+__device__ __forceinline__ bool tri_uv(const RaySetup& r, float4 a, float4 b, float4 c, float id, float bx, float by,
+                                       float bz, float a00, float a10, float& u, float& v) {
+    const float m00 = a.w, m10 = b.x, m20 = b.y;
+    const float m01 = b.z, m11 = b.w, m21 = c.x;
+    const float m02 = -r.dx, m12 = -r.dy, m22 = -r.dz;
+    (void)m20; (void)m21;
+    const float a01 = -subr(mulr(m01, m22), mulr(m21, m02));
+    const float a02 = subr(mulr(m01, m12), mulr(m11, m02));
+    const float a11 = subr(mulr(m00, m22), mulr(m20, m02));
+    const float a12 = -subr(mulr(m00, m12), mulr(m10, m02));
+    u = addr(addr(mulr(mulr(a00, id), bx), mulr(mulr(a01, id), by)), mulr(mulr(a02, id), bz));
+    v = addr(addr(mulr(mulr(a10, id), bx), mulr(mulr(a11, id), by)), mulr(mulr(a12, id), bz));
+    return !(u < 0.0f || v < 0.0f || addr(u, v) > 1.0f);
+}
+
+struct Stack {
+    int* s_node;   // shared: [SMEM_STACK][TRACE_THREADS]
+    float* s_dist;
+    int l_node[LOCAL_STACK];
+    float l_dist[LOCAL_STACK];
+    int sp;
+    __device__ __forceinline__ void push(int node, float dist) {
+        if (sp < SMEM_STACK) {
+            s_node[sp * TRACE_THREADS] = node;
+            s_dist[sp * TRACE_THREADS] = dist;
+        } else {
+            l_node[sp - SMEM_STACK] = node;
+            l_dist[sp - SMEM_STACK] = dist;
+        }
+        sp++;
+    }
+    __device__ __forceinline__ void pop(int& node, float& dist) {
+        sp--;
+        if (sp < SMEM_STACK) {
+            node = s_node[sp * TRACE_THREADS];
+            dist = s_dist[sp * TRACE_THREADS];
+        } else {
+            node = l_node[sp - SMEM_STACK];
+            dist = l_dist[sp - SMEM_STACK];
+        }
+    }
+};
+
+#define ORT_CSWAP(da, ca, db, cb)            \
+    {                                        \
+        bool sw_ = db < da;                  \
+        float td_ = sw_ ? db : da;           \
+        int tc_ = sw_ ? cb : ca;             \
+        db = sw_ ? da : db; cb = sw_ ? ca : cb; \
+        da = td_; ca = tc_;                  \
+    }
+
+// ------------------------------------------------------------------------------------------------
+// k_trace: closest hit (cast_ray, raytracer.odin:416).  Persistent warps pull 32-ray packets from
+// the compacted queue with one atomic per packet.  hits[pos] = (t without the trailing +RAY_EPS,
+// u, v, triangle id as int bits; -1 = miss).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TRACE_THREADS)
+k_trace(const SceneDev s, const float4* __restrict__ qo, const float4* __restrict__ qd,
+        const uint32_t* __restrict__ n_ptr, uint32_t* __restrict__ work_ctr, float4* __restrict__ hits) {
+    __shared__ int sh_node[SMEM_STACK * TRACE_THREADS];
+    __shared__ float sh_dist[SMEM_STACK * TRACE_THREADS];
+    const uint32_t n = *n_ptr;
+    const int lane = threadIdx.x & 31;
+    Stack st;
+    st.s_node = sh_node + threadIdx.x;
+    st.s_dist = sh_dist + threadIdx.x;
+    const float best_pad = 1.0f + 7.62939453125e-06f; // 1 + 2^-17: distance culling margin
+
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(work_ctr, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const uint32_t pos = base + lane;
+        if (pos < n) {
+            const RaySetup r = make_ray(ldg4(qo + pos), ldg4(qd + pos), s.pad_scale);
+            float best = __int_as_float(0x7f800000); // max_dist = +inf (raytracer.odin:435)
+            float hu = 0.0f, hv = 0.0f;
+            int htri = -1;
+            st.sp = 0;
+            int cur = 0; // root
+            for (;;) {
+                while (cur >= 0) {
+                    const float4* nd = s.nodes + (size_t)cur * 8;
+                    const float4 nxp = ldg4(nd + r.sx), fxp = ldg4(nd + (r.sx ^ 1));
+                    const float4 nyp = ldg4(nd + r.sy), fyp = ldg4(nd + (r.sy ^ 1));
+                    const float4 nzp = ldg4(nd + r.sz), fzp = ldg4(nd + (r.sz ^ 1));
+                    const int4 ch = __ldg(reinterpret_cast<const int4*>(nd + 6));
+                    const float lim = best * best_pad;
+                    float d0, d1, d2, d3;
+                    int c0 = ch.x, c1 = ch.y, c2 = ch.z, c3 = ch.w;
+#define ORT_BOX(k, D, C)                                                                          \
+    {                                                                                             \
+        float tn = fmaxf(fmaxf(fmaf(nxp.k, r.ix, r.nx), fmaf(nyp.k, r.iy, r.ny)),                 \
+                         fmaxf(fmaf(nzp.k, r.iz, r.nz), 0.0f));                                   \
+        float tf = fminf(fminf(fmaf(fxp.k, r.ix, r.fx), fmaf(fyp.k, r.iy, r.fy)),                 \
+                         fminf(fmaf(fzp.k, r.iz, r.fz), lim));                                    \
+        D = (tn <= tf && C != WIDE_EMPTY) ? tn : __int_as_float(0x7f800000);                      \
+    }
+                    ORT_BOX(x, d0, c0) ORT_BOX(y, d1, c1) ORT_BOX(z, d2, c2) ORT_BOX(w, d3, c3)
+#undef ORT_BOX
+                    const float inf = __int_as_float(0x7f800000);
+                    const int nh = (d0 < inf) + (d1 < inf) + (d2 < inf) + (d3 < inf);
+                    ORT_CSWAP(d0, c0, d1, c1) ORT_CSWAP(d2, c2, d3, c3) ORT_CSWAP(d0, c0, d2, c2)
+                    ORT_CSWAP(d1, c1, d3, c3) ORT_CSWAP(d1, c1, d2, c2)
+                    if (nh == 0) {
+                        // pop, skipping entries the current best already culls
+                        cur = WIDE_EMPTY;
+                        while (st.sp > 0) {
+                            int nd2; float dd;
+                            st.pop(nd2, dd);
+                            if (dd <= best * best_pad) { cur = nd2; break; }
+                        }
+                    } else {
+                        if (nh > 3) st.push(c3, d3);
+                        if (nh > 2) st.push(c2, d2);
+                        if (nh > 1) st.push(c1, d1);
+                        cur = c0;
+                    }
+                }
+                if (cur == WIDE_EMPTY) break;
+                // leaf: cast_ray_through_trigs (raytracer.odin:351-369), reference order, first wins ties
+                {
+                    const uint32_t code = (uint32_t)~cur;
+                    const uint32_t first = code >> 3, cnt = code & 7u;
+                    for (uint32_t i = 0; i < cnt; i++) {
+                        const float4* tp = s.tris + (size_t)(first + i) * 3;
+                        const float4 a = ldg4(tp), b = ldg4(tp + 1), c = ldg4(tp + 2);
+                        float id, bx, by, bz, t, a00, a10;
+                        tri_det_t(r, a, b, c, id, bx, by, bz, t, a00, a10);
+                        if (t > 0.0f && t < best) { // raytracer.odin:360
+                            float u, v;
+                            if (tri_uv(r, a, b, c, id, bx, by, bz, a00, a10, u, v)) {
+                                best = t; hu = u; hv = v; htri = (int)(first + i);
+                            }
+                        }
+                    }
+                }
+                cur = WIDE_EMPTY;
+                while (st.sp > 0) {
+                    int nd2; float dd;
+                    st.pop(nd2, dd);
+                    if (dd <= best * best_pad) { cur = nd2; break; }
+                }
+                if (cur == WIDE_EMPTY) break;
+            }
+            hits[pos] = make_float4(htri >= 0 ? best : 0.0f, hu, hv, __int_as_float(htri));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_light: surface_sampling_pdf_bvh_sum (shading.odin:62-94) — every light triangle the
+// unbounded ray hits with t >= 0 contributes (2/|u x v|) * t^2 / |ng.d|.  lsum[pos] = the sum
+// (the division by the light count, shading.odin:99, happens in k_shade).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TRACE_THREADS)
+k_light(const SceneDev s, const float4* __restrict__ qo, const float4* __restrict__ qd,
+        const uint32_t* __restrict__ n_ptr, uint32_t* __restrict__ work_ctr, float* __restrict__ lsum) {
+    __shared__ int sh_node[SMEM_STACK * TRACE_THREADS];
+    __shared__ float sh_dist[SMEM_STACK * TRACE_THREADS];
+    const uint32_t n = *n_ptr;
+    const int lane = threadIdx.x & 31;
+    Stack st;
+    st.s_node = sh_node + threadIdx.x;
+    st.s_dist = sh_dist + threadIdx.x;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(work_ctr, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const uint32_t pos = base + lane;
+        if (pos < n) {
+            const RaySetup r = make_ray(ldg4(qo + pos), ldg4(qd + pos), s.lpad_scale);
+            float sum = 0.0f;
+            st.sp = 0;
+            int cur = 0;
+            for (;;) {
+                while (cur >= 0) {
+                    const float4* nd = s.lnodes + (size_t)cur * 8;
+                    const float4 nxp = ldg4(nd + r.sx), fxp = ldg4(nd + (r.sx ^ 1));
+                    const float4 nyp = ldg4(nd + r.sy), fyp = ldg4(nd + (r.sy ^ 1));
+                    const float4 nzp = ldg4(nd + r.sz), fzp = ldg4(nd + (r.sz ^ 1));
+                    const int4 ch = __ldg(reinterpret_cast<const int4*>(nd + 6));
+                    int next = WIDE_EMPTY;
+#define ORT_BOX(k, C)                                                                             \
+    {                                                                                             \
+        float tn = fmaxf(fmaxf(fmaf(nxp.k, r.ix, r.nx), fmaf(nyp.k, r.iy, r.ny)),                 \
+                         fmaxf(fmaf(nzp.k, r.iz, r.nz), 0.0f));                                   \
+        float tf = fminf(fminf(fmaf(fxp.k, r.ix, r.fx), fmaf(fyp.k, r.iy, r.fy)),                 \
+                         fmaf(fzp.k, r.iz, r.fz));                                                \
+        if (tn <= tf && C != WIDE_EMPTY) {                                                        \
+            if (next != WIDE_EMPTY) st.push(next, 0.0f);                                          \
+            next = C;                                                                             \
+        }                                                                                         \
+    }
+                    ORT_BOX(x, ch.x) ORT_BOX(y, ch.y) ORT_BOX(z, ch.z) ORT_BOX(w, ch.w)
+#undef ORT_BOX
+                    if (next == WIDE_EMPTY && st.sp > 0) { float dd; st.pop(next, dd); }
+                    cur = next;
+                }
+                if (cur == WIDE_EMPTY) break;
+                {
+                    const uint32_t code = (uint32_t)~cur;
+                    const uint32_t first = code >> 3, cnt = code & 7u;
+                    for (uint32_t i = 0; i < cnt; i++) {
+                        const float4* tp = s.ltris + (size_t)(first + i) * 3;
+                        const float4 a = ldg4(tp), b = ldg4(tp + 1), c = ldg4(tp + 2);
+                        float id, bx, by, bz, t, a00, a10, u, v;
+                        tri_det_t(r, a, b, c, id, bx, by, bz, t, a00, a10);
+                        // reference: intersect returns t = -1 when (u,v) is outside, then `!(t >= 0)` skips
+                        if (t >= 0.0f && tri_uv(r, a, b, c, id, bx, by, bz, a00, a10, u, v)) {
+                            const float4 L = ldg4(s.llight + (first + i));
+                            const float weight = (t * t) / fabsf(L.x * r.dx + L.y * r.dy + L.z * r.dz);
+                            sum += L.w * weight;
+                        }
+                    }
+                }
+                cur = WIDE_EMPTY;
+                if (st.sp > 0) { float dd; st.pop(cur, dd); }
+                if (cur == WIDE_EMPTY) break;
+            }
+            lsum[pos] = sum;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_raygen: primary rays (raytracer.odin:580-586).  slot = s_local * npix + (py*w + px).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ f3 primary_dir(const RenderParams& p, uint32_t px, uint32_t py, uint32_t pix, uint64_t sample) {
+    const Philox4 rr = philox4x32_10(pix, (uint32_t)sample, (uint32_t)(sample >> 32), 0u, (uint32_t)p.seed,
+                                     (uint32_t)(p.seed >> 32));
+    const float x = addr((float)px, u01(rr.r0));
+    const float y = addr((float)py, u01(rr.r1));
+    // (M * {x, y, 0, 1}).xyz, each row summed left to right
+    float v[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        const float* m = p.M + 4 * r;
+        v[r] = addr(addr(addr(mulr(m[0], x), mulr(m[1], y)), mulr(m[2], 0.0f)), mulr(m[3], 1.0f));
+    }
+    const float len = sqrtr(addr(addr(mulr(v[0], v[0]), mulr(v[1], v[1])), mulr(v[2], v[2])));
+    return mk3(divr(v[0], len), divr(v[1], len), divr(v[2], len));
+}
+
+__global__ void k_raygen(const RenderParams p, float4* __restrict__ qo, float4* __restrict__ qd,
+                         uint32_t* __restrict__ count0) {
+    const uint32_t n = p.n_batch_samples * p.npix;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *count0 = n;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t s_local = i / p.npix, pix = i - s_local * p.npix;
+        const uint32_t py = pix / p.w, px = pix - py * p.w;
+        const f3 d = primary_dir(p, px, py, pix, p.sample_base + s_local);
+        qo[i] = make_float4(p.cam_pos[0], p.cam_pos[1], p.cam_pos[2], __uint_as_float(i));
+        qd[i] = make_float4(d.x, d.y, d.z, 0.0f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// textures (textures.odin:79-135): texel fetches through texture objects (point, unnormalised),
+// repeat wrap by floored modulo, no half-texel offset, bilinear weights in f32.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int wrap_i(float f, int m) {
+    long long i = (long long)f;
+    long long r = i % m;
+    return (int)(r < 0 ? r + m : r);
+}
+__device__ __forceinline__ float lerp1(float a, float b, float t) { return a * (1.0f - t) + b * t; }
+__device__ __forceinline__ float4 lerp4(float4 a, float4 b, float t) {
+    return make_float4(lerp1(a.x, b.x, t), lerp1(a.y, b.y, t), lerp1(a.z, b.z, t), lerp1(a.w, b.w, t));
+}
+__device__ __forceinline__ float4 texture_sample(const DevTexture& tx, bool srgb, float cu, float cv) {
+    const cudaTextureObject_t obj = srgb ? tx.linear : tx.raw;
+    const float pcx = cu * (float)tx.w, pcy = cv * (float)tx.h;
+    const float lox = floorf(pcx), loy = floorf(pcy);
+    const float hix = ceilf(pcx), hiy = ceilf(pcy);
+    const float tx_ = pcx - lox, ty_ = pcy - loy;
+    const float x0 = (float)wrap_i(lox, tx.w) + 0.5f, y0 = (float)wrap_i(loy, tx.h) + 0.5f;
+    const float x1 = (float)wrap_i(hix, tx.w) + 0.5f, y1 = (float)wrap_i(hiy, tx.h) + 0.5f;
+    const float4 p00 = tex2D<float4>(obj, x0, y0);
+    const float4 p01 = tex2D<float4>(obj, x0, y1);
+    const float4 p10 = tex2D<float4>(obj, x1, y0);
+    const float4 p11 = tex2D<float4>(obj, x1, y1);
+    return lerp4(lerp4(p00, p01, ty_), lerp4(p10, p11, ty_), tx_);
+}
+
+// ------------------------------------------------------------------------------------------------
+// shading.odin
+// ------------------------------------------------------------------------------------------------
+struct Quat {
+    float w, x, y, z;
+};
+__device__ __forceinline__ f3 quat_mul_vec(Quat q, f3 v) { // linalg.mul(quaternion, vector)
+    const f3 qv = mk3(q.x, q.y, q.z);
+    const f3 t = cross3(2.0f * qv, v);
+    return v + q.w * t + cross3(qv, t);
+}
+__device__ __forceinline__ Quat vndf_rotation(f3 n) { // shading.odin:104-106
+    const float w = sqrtf((1.0f + n.z) / 2.0f);
+    if (w > 0.0f) return {w, -n.y / (2.0f * w), n.x / (2.0f * w), 0.0f};
+    return {0.0f, 1.0f, 0.0f, 0.0f};
+}
+__device__ __forceinline__ Quat qconj(Quat q) { return {q.w, -q.x, -q.y, -q.z}; }
+
+__device__ f3 vndf_sampling(f3 n, f3 omega, float alpha, float u1, float u2) { // shading.odin:102-122
+    const Quat rot = vndf_rotation(n);
+    const f3 V = quat_mul_vec(qconj(rot), omega);
+    const f3 Vh = normalize3(mk3(alpha * V.x, alpha * V.y, V.z));
+    const float len = hypotf(Vh.x, Vh.y);
+    const f3 T1 = len == 0.0f ? mk3(1, 0, 0) : mk3(-Vh.y / len, Vh.x / len, 0.0f);
+    const f3 T2 = cross3(Vh, T1);
+    const float r = sqrtf(u1);
+    const float phi = TAU_F * u2;
+    float t1, t2;
+    sincosf(phi, &t1, &t2);
+    t1 *= r;
+    t2 *= r;
+    const float s = 0.5f * (1.0f + Vh.z);
+    t2 = (1.0f - s) * sqrtf(1.0f - sq(t1)) + s * t2;
+    const f3 Nh = t1 * T1 + t2 * T2 + Vh * sqrtf(omax(0.0f, 1.0f - sq(t1) - sq(t2)));
+    const f3 Ne = normalize3(mk3(alpha * Nh.x, alpha * Nh.y, omax(0.0f, Nh.z)));
+    return quat_mul_vec(rot, Ne);
+}
+__device__ float vndf_sampling_pdf(f3 n, f3 omega, float alpha, f3 L) { // shading.odin:124-137
+    const f3 Ne = normalize3(omega + L);
+    const Quat rot = vndf_rotation(n);
+    const f3 V = quat_mul_vec(qconj(rot), omega);
+    const f3 N = quat_mul_vec(qconj(rot), Ne);
+    const float alpha2 = sq(alpha);
+    const float lambda = (-1.0f + sqrtf(1.0f + alpha2 * (sq(V.x) + sq(V.y)) / sq(V.z))) * 0.5f;
+    const float G1 = 1.0f / (1.0f + lambda);
+    const float D = 1.0f / (PI_F * alpha2 * sq(sq(N.x / alpha) + sq(N.y / alpha) + sq(N.z)));
+    const float normal = G1 * omax(0.0f, dot3(V, N)) * D / V.z;
+    return normal / (4.0f * dot3(L, Ne));
+}
+__device__ __forceinline__ float smith_ggx(f3 n, f3 x, float alpha2) { // shading.odin:187-190
+    const float c = dot3(n, x);
+    return 2.0f * omax(c, 0.0f) / (c + sqrtf(alpha2 + (1.0f - alpha2) * sq(c)));
+}
+__device__ f3 brdf_cos(f3 color, f3 N, float metallic, float roughness, f3 in_d, f3 L) { // shade, shading.odin:164-204
+    const float alpha = sq(roughness);
+    const float alpha2 = sq(alpha);
+    const f3 V = -in_d;
+    const f3 H = normalize3(L + V);
+    const float cosine = dot3(L, N);
+    const float fb = powf(1.0f - dot3(H, L), 5.0f);
+    const float f_ds = 0.04f + 0.96f * fb;
+    const f3 f_m = color + (mk3(1, 1, 1) - color) * fb;
+    const float hn = dot3(H, N);
+    const float step = hn < 0.0f ? 0.0f : 1.0f;
+    const float Dt = alpha2 * step / (PI_F * sq((alpha2 - 1.0f) * sq(hn) + 1.0f));
+    const float G = smith_ggx(N, L, alpha2) * smith_ggx(N, V, alpha2);
+    const float ct = Dt * G / (4.0f * dot3(V, N));
+    const f3 spec = ct * mk3(1, 1, 1);
+    const f3 diff = color * omax(cosine, 0.0f) / PI_F;
+    const f3 met = spec * f_m;
+    const f3 diel = diff * (1.0f - f_ds) + spec * f_ds;
+    return diel * (1.0f - metallic) + met * metallic;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_shade: one wavefront step of raytrace (raytracer.odin:432-500) in iterative form.
+// Path state by slot:  st_a = (T.rgb, cosine pdf)   st_b = (value.rgb, vndf pdf term)
+//                      st_c = (L.rgb, -)            with L = sum_k T_k * emission_k.
+// For bounce > 0 the pending (value, pdf) of the previous hit is completed first: the light-BVH
+// sum of the ray just traced is the missing third of pdf (shading.odin:153-162), then
+// `norm_l1(value)/pdf > 1e-5` (raytracer.odin:495) decides whether this hit counts at all.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_shade(const SceneDev s, const RenderParams p, const int bounce, const float4* __restrict__ qo_in,
+        const float4* __restrict__ qd_in, const float4* __restrict__ hits, const float* __restrict__ lsum,
+        const uint32_t* __restrict__ n_in_ptr, float4* __restrict__ qo_out, float4* __restrict__ qd_out,
+        uint32_t* __restrict__ n_out_ptr, float4* __restrict__ st_a, float4* __restrict__ st_b,
+        float4* __restrict__ st_c) {
+    const uint32_t n_in = *n_in_ptr;
+    const int lane = threadIdx.x & 31;
+    const bool has_lights = s.n_lights > 0;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n_in; base += gridDim.x * blockDim.x) {
+        const uint32_t pos = base + threadIdx.x;
+        bool emit = false;
+        float4 out_o = make_float4(0, 0, 0, 0), out_d = make_float4(0, 0, 0, 0);
+        if (pos < n_in) {
+            const float4 o4 = qo_in[pos];
+            const float4 d4 = qd_in[pos];
+            const float4 h4 = hits[pos];
+            const uint32_t slot = __float_as_uint(o4.w);
+            const f3 in_d = mk3(d4.x, d4.y, d4.z);
+            f3 T = mk3(1, 1, 1), L = mk3(0, 0, 0);
+            bool alive = true;
+            if (bounce > 0) {
+                const float4 a = st_a[slot], b = st_b[slot], c = st_c[slot];
+                const f3 value = mk3(b.x, b.y, b.z);
+                L = mk3(c.x, c.y, c.z);
+                // pdf (shading.odin:158-161): (cosine + light + vndf * (1 | 2)) / 3
+                const float lp = has_lights ? lsum[pos] / (float)s.n_lights : 0.0f;
+                const float pdf = (a.w + lp + b.w) / 3.0f;
+                if (norm_l1(value) / pdf > 1e-5f) T = mk3(a.x, a.y, a.z) * value / pdf;
+                else alive = false; // exitance = emission only: L already holds it
+            }
+            if (alive) {
+                const int tri = __float_as_int(h4.w);
+                if (tri < 0) {
+                    // miss: equirectangular env lookup (raytracer.odin:437-446), black without a map
+                    if (s.has_env) {
+                        const float tu = 0.5f + atan2f(in_d.z, in_d.x) / TAU_F;
+                        const float tv = 0.5f - asinf(in_d.y) / PI_F;
+                        const float4 e = texture_sample(s.env, false, tu, tv);
+                        L = L + T * mk3(e.x, e.y, e.z);
+                    }
+                    st_c[slot] = make_float4(L.x, L.y, L.z, 0.0f);
+                } else {
+                    const float u = h4.y, v = h4.z;
+                    const float4* ts = s.tshade + (size_t)tri * 4;
+                    const float4 s0 = ldg4(ts), s1 = ldg4(ts + 1), s2 = ldg4(ts + 2);
+                    const int4 s3 = __ldg(reinterpret_cast<const int4*>(ts + 3));
+                    const DevMaterial m = s.mats[s3.x];
+                    const float4* tp = s.tris + (size_t)tri * 3;
+                    const float4 ta = ldg4(tp), tb = ldg4(tp + 1), tc = ldg4(tp + 2);
+                    // p = trig.p + trig.u*u + trig.v*v (raytracer.odin:456), individually rounded
+                    const f3 P = mk3(addr(addr(ta.x, mulr(ta.w, u)), mulr(tb.z, v)),
+                                     addr(addr(ta.y, mulr(tb.x, u)), mulr(tb.w, v)),
+                                     addr(addr(ta.z, mulr(tb.y, u)), mulr(tc.x, v)));
+                    const float w0 = 1.0f - u - v;
+                    const bool any_tex = m.color_tex >= 0 || m.emission_tex >= 0 || m.mr_tex >= 0 || m.normal_tex >= 0;
+                    float tcx = 0.0f, tcy = 0.0f;
+                    if (any_tex) {
+                        const float4 uv0 = ldg4(s.tuv + (size_t)tri * 2), uv1 = ldg4(s.tuv + (size_t)tri * 2 + 1);
+                        tcx = uv0.x * w0 + uv0.z * u + uv1.x * v; // raytracer.odin:454
+                        tcy = uv0.y * w0 + uv0.w * u + uv1.y * v;
+                    }
+                    float4 mr = make_float4(1, 1, 1, 1);
+                    if (m.mr_tex >= 0) mr = texture_sample(s.texs[m.mr_tex], false, tcx, tcy);
+                    const f3 n_interp = mk3(s0.x, s0.y, s0.z) * w0 + mk3(s1.x, s1.y, s1.z) * u + mk3(s2.x, s2.y, s2.z) * v;
+                    f3 N;
+                    if (m.normal_tex >= 0) { // raytracer.odin:458-470
+                        const float4* tt = s.ttan + (size_t)tri * 3;
+                        const float4 g0 = ldg4(tt), g1 = ldg4(tt + 1), g2 = ldg4(tt + 2);
+                        float t4x = g0.x * w0 + g1.x * u + g2.x * v, t4y = g0.y * w0 + g1.y * u + g2.y * v;
+                        float t4z = g0.z * w0 + g1.z * u + g2.z * v, t4w = g0.w * w0 + g1.w * u + g2.w * v;
+                        const float l4 = sqrtf(t4x * t4x + t4y * t4y + t4z * t4z + t4w * t4w); // [4]f32 normalize
+                        t4x /= l4; t4y /= l4; t4z /= l4; t4w /= l4;
+                        const f3 lx = mk3(t4x, t4y, t4z);
+                        const f3 lz = normalize3(n_interp);
+                        const f3 ly = cross3(lz, lx) * t4w;
+                        const float4 ns = texture_sample(s.texs[m.normal_tex], false, tcx, tcy);
+                        const f3 ln = mk3(ns.x, ns.y, ns.z) * 2.0f - mk3(1, 1, 1);
+                        N = normalize3(mk3(lx.x * ln.x + ly.x * ln.y + lz.x * ln.z, lx.y * ln.x + ly.y * ln.y + lz.y * ln.z,
+                                           lx.z * ln.x + ly.z * ln.y + lz.z * ln.z));
+                    } else {
+                        N = normalize3(n_interp); // raytracer.odin:472
+                    }
+                    f3 color = mk3(m.color[0], m.color[1], m.color[2]);
+                    f3 emission = mk3(m.emission[0], m.emission[1], m.emission[2]);
+                    if (m.color_tex >= 0) {
+                        const float4 c = texture_sample(s.texs[m.color_tex], true, tcx, tcy);
+                        color = color * mk3(c.x, c.y, c.z);
+                    }
+                    if (m.emission_tex >= 0) {
+                        const float4 c = texture_sample(s.texs[m.emission_tex], true, tcx, tcy);
+                        emission = emission * mk3(c.x, c.y, c.z);
+                    }
+                    const float roughness = omax(m.roughness * mr.y, 0.03f); // raytracer.odin:480
+                    const float metallic = m.metallic * mr.z;
+                    // inside = dot(ng, d) > 0 (raytracer.odin:148), flips the shading normal (:485-488)
+                    const float ngd = addr(addr(mulr(s0.w, in_d.x), mulr(s1.w, in_d.y)), mulr(s2.w, in_d.z));
+                    if (ngd > 0.0f) N = -N;
+                    L = L + T * emission;
+                    bool cont = bounce + 1 < p.ray_depth; // raytrace(.., depth_left - 1) with depth_left == 1 returns 0
+                    f3 nd = mk3(0, 0, 0), value = mk3(0, 0, 0);
+                    float cos_pdf = 0.0f, vndf_term = 0.0f;
+                    if (cont) {
+                        // sample (shading.odin:139-151)
+                        const uint32_t s_local = slot / p.npix, pix = slot - s_local * p.npix;
+                        const uint64_t smp = p.sample_base + s_local;
+                        const Philox4 rr = philox4x32_10(pix, (uint32_t)smp, (uint32_t)(smp >> 32), 1u + (uint32_t)bounce,
+                                                         (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+                        const float tsel = u01(rr.r0);
+                        if (tsel <= 0.33333f) {
+                            const float phi = u01(rr.r1) * (TAU_F - 0.0f) + 0.0f; // sphere_uniform shading.odin:9-15
+                            const float z = u01(rr.r2) * (1.0f - -1.0f) + -1.0f;
+                            float sx, sy;
+                            sincosf(phi, &sx, &sy);
+                            const float radius = sqrtf(1.0f - sq(z));
+                            nd = normalize3(mk3(sx * radius, sy * radius, z) + N);
+                        } else if (tsel < 0.666666f && has_lights) {
+                            const uint32_t idx = (uint32_t)(((uint64_t)rr.r1 * (uint64_t)(uint32_t)s.n_lights) >> 32);
+                            const float4* lp = s.ltris + (size_t)idx * 3;
+                            const float4 la = ldg4(lp), lb = ldg4(lp + 1), lc = ldg4(lp + 2);
+                            float su = u01(rr.r2) * (1.0f - 0.0f) + 0.0f, sv = u01(rr.r3) * (1.0f - 0.0f) + 0.0f;
+                            if (su + sv > 1.0f) { su = 1.0f - su; sv = 1.0f - sv; }
+                            const f3 world = mk3(la.x, la.y, la.z) + su * mk3(la.w, lb.x, lb.y) + sv * mk3(lb.z, lb.w, lc.x);
+                            nd = normalize3(world - P);
+                        } else {
+                            const f3 hn = vndf_sampling(N, -in_d, sq(roughness), u01(rr.r1), u01(rr.r2));
+                            nd = in_d - 2.0f * dot3(hn, in_d) * hn;
+                        }
+                        value = brdf_cos(color, N, metallic, roughness, in_d, nd);
+                        // norm_l1(value)/pdf > 1e-5 can only hold for norm_l1(value) > 0
+                        if (!(norm_l1(value) > 0.0f)) cont = false;
+                    }
+                    if (cont) {
+                        cos_pdf = omax(dot3(N, nd) / PI_F, 0.0f); // shading.odin:37-39
+                        vndf_term = vndf_sampling_pdf(N, -in_d, sq(roughness), nd) * (has_lights ? 1.0f : 2.0f);
+                        st_a[slot] = make_float4(T.x, T.y, T.z, cos_pdf);
+                        st_b[slot] = make_float4(value.x, value.y, value.z, vndf_term);
+                        emit = true;
+                        out_o = make_float4(P.x, P.y, P.z, o4.w);
+                        out_d = make_float4(nd.x, nd.y, nd.z, 0.0f);
+                    }
+                    st_c[slot] = make_float4(L.x, L.y, L.z, 0.0f);
+                }
+            }
+        }
+        // queue compaction: warp ballot + prefix popcount + one atomic per warp
+        const unsigned mask = __ballot_sync(0xffffffffu, emit);
+        if (mask) {
+            const int leader = __ffs(mask) - 1;
+            uint32_t wbase = 0;
+            if (lane == leader) wbase = atomicAdd(n_out_ptr, (uint32_t)__popc(mask));
+            wbase = __shfl_sync(0xffffffffu, wbase, leader);
+            if (emit) {
+                const uint32_t q = wbase + __popc(mask & ((1u << lane) - 1u));
+                qo_out[q] = out_o;
+                qd_out[q] = out_d;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_resolve: rc_set_pixel (main.odin:89-102) for every sample of the wave, in sample order.
+// accum planes: total.rgb | total_squared.rgb | count | reserved, index (H-1-y)*W + x.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_resolve(const RenderParams p, const float4* __restrict__ st_c, float* __restrict__ accum,
+                          float* __restrict__ first, float* __restrict__ last, const int write_first,
+                          const int write_last) {
+    const uint32_t npix = p.npix;
+    for (uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += gridDim.x * blockDim.x) {
+        const uint32_t py = pix / p.w, px = pix - py * p.w;
+        const uint32_t i = (p.h - py - 1) * p.w + px;
+        float tr = accum[i], tg = accum[npix + i], tb = accum[2 * npix + i];
+        float qr = accum[3 * npix + i], qg = accum[4 * npix + i], qb = accum[5 * npix + i];
+        float4 c = make_float4(0, 0, 0, 0);
+        for (uint32_t sl = 0; sl < p.n_batch_samples; sl++) {
+            c = st_c[(size_t)sl * npix + pix];
+            if (sl == 0 && write_first) { first[i] = c.x; first[npix + i] = c.y; first[2 * npix + i] = c.z; }
+            tr += c.x; tg += c.y; tb += c.z;
+            qr += c.x * c.x; qg += c.y * c.y; qb += c.z * c.z;
+        }
+        accum[i] = tr; accum[npix + i] = tg; accum[2 * npix + i] = tb;
+        accum[3 * npix + i] = qr; accum[4 * npix + i] = qg; accum[5 * npix + i] = qb;
+        accum[6 * npix + i] += (float)p.n_batch_samples;
+        if (write_last) { last[i] = c.x; last[npix + i] = c.y; last[2 * npix + i] = c.z; }
+    }
+}
+
+// counters: [0 .. D] queue sizes per bounce.  stats: [0] closest rays, [1] light rays, [2] paths
+__global__ void k_stats(const uint32_t* __restrict__ counts, const int depth, const int has_lights,
+                        unsigned long long* __restrict__ stats) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        unsigned long long rays = 0, lrays = 0;
+        for (int k = 0; k < depth; k++) {
+            rays += counts[k];
+            if (k > 0 && has_lights) lrays += counts[k];
+        }
+        stats[0] += rays;
+        stats[1] += lrays;
+        stats[2] += counts[0];
+    }
+}
+
+// ---- probes / packing ---------------------------------------------------------------------------
+__global__ void k_pack_rays(const float* __restrict__ rays6, const uint32_t n, float4* __restrict__ qo,
+                            float4* __restrict__ qd, uint32_t* __restrict__ count0) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *count0 = n;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        qo[i] = make_float4(rays6[6 * i], rays6[6 * i + 1], rays6[6 * i + 2], __uint_as_float(i));
+        qd[i] = make_float4(rays6[6 * i + 3], rays6[6 * i + 4], rays6[6 * i + 5], 0.0f);
+    }
+}
+// ort_hit = {t, u, v, tri, material, inside}
+__global__ void k_unpack_hits(const SceneDev s, const float4* __restrict__ hits, const float4* __restrict__ qd,
+                              const uint32_t n, float* __restrict__ out6) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 h = hits[i];
+        const int tri = __float_as_int(h.w);
+        int mat = -1, inside = 0;
+        if (tri >= 0) {
+            const float4* ts = s.tshade + (size_t)tri * 4;
+            const float4 s0 = ldg4(ts), s1 = ldg4(ts + 1), s2 = ldg4(ts + 2);
+            mat = __ldg(reinterpret_cast<const int4*>(ts + 3)).x;
+            const float4 d = qd[i];
+            inside = addr(addr(mulr(s0.w, d.x), mulr(s1.w, d.y)), mulr(s2.w, d.z)) > 0.0f ? 1 : 0;
+        }
+        out6[6 * i + 0] = addr(h.x, RAY_EPS); // hit.t += RAY_EPS (raytracer.odin:428)
+        out6[6 * i + 1] = h.y;
+        out6[6 * i + 2] = h.z;
+        out6[6 * i + 3] = __int_as_float(tri);
+        out6[6 * i + 4] = __int_as_float(mat);
+        out6[6 * i + 5] = __int_as_float(inside);
+    }
+}
+__global__ void k_unpack_rays(const float4* __restrict__ qo, const float4* __restrict__ qd, const uint32_t n,
+                              float* __restrict__ out6) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 o = qo[i], d = qd[i];
+        out6[6 * i] = o.x; out6[6 * i + 1] = o.y; out6[6 * i + 2] = o.z;
+        out6[6 * i + 3] = d.x; out6[6 * i + 4] = d.y; out6[6 * i + 5] = d.z;
+    }
+}
+__global__ void k_scale(float* __restrict__ x, const uint32_t n, const float inv) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) x[i] = x[i] / inv;
+}
+
+// planar accumulators (+ optional first/last planes) -> Sample_Stats AoS (13 words / pixel)
+__global__ void k_pack_stats(const float* __restrict__ accum, const float* __restrict__ first,
+                             const float* __restrict__ last, const uint32_t npix, uint32_t* __restrict__ out13) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
+        uint32_t* o = out13 + (size_t)i * 13;
+        for (int c = 0; c < 3; c++) {
+            o[c] = __float_as_uint(first ? first[c * npix + i] : 0.0f);
+            o[4 + c] = __float_as_uint(last ? last[c * npix + i] : 0.0f);
+            o[7 + c] = __float_as_uint(accum[c * npix + i]);
+            o[10 + c] = __float_as_uint(accum[(3 + c) * npix + i]);
+        }
+        o[3] = (uint32_t)accum[6 * npix + i];
+    }
+}
+
+// get_rgb_image, mode Mean (output.odin:21-80)
+__global__ void k_tonemap(const float* __restrict__ accum, const uint32_t npix, uint8_t* __restrict__ rgb) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
+        const float cnt = accum[6 * npix + i];
+        for (int c = 0; c < 3; c++) {
+            float x = omax(accum[c * npix + i] / cnt, 0.0f);
+            float tm = (x * (2.51f * x + 0.03f)) / (x * (2.43f * x + 0.59f) + 0.14f);
+            tm = fminf(fmaxf(tm, 0.0f), 1.0f);
+            const float g = powf(tm, (float)(1.0 / 2.2));
+            rgb[3 * (size_t)i + c] = (uint8_t)roundf(g * 255.0f);
+        }
+    }
+}
+
+} // namespace ort

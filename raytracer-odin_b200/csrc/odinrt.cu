@@ -1,0 +1,714 @@
+// odinrt.cu — context, scene upload, wavefront scheduling and the C ABI of libodinrt_b200.so
+// (include/odinrt_b200.h).  Replaces render_scene / render_task (raytracer.odin:528-665): the
+// atomic tile counter and OS threads become waves of (pixel x sample) paths advanced one bounce
+// at a time by k_trace / k_light / k_shade, with queue sizes living on the device so a whole wave
+// is enqueued without any host synchronisation.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace ort;
+
+namespace {
+thread_local std::string g_create_error;
+}
+
+struct ort_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    uint64_t seed = 0;
+    int64_t capacity_cfg = 0;
+    std::string err;
+
+    // scene
+    bool has_scene = false;
+    SceneDev sd{};
+    ort_camera cam{};
+    std::vector<void*> scene_allocs;
+    std::vector<cudaArray_t> scene_arrays;
+    std::vector<cudaTextureObject_t> scene_textures;
+    int64_t n_tris = 0, n_ltris = 0;
+    WideBVH wide, lwide;
+    int64_t scene_bytes = 0;
+
+    // path buffers (one wave)
+    int64_t capacity = 0;
+    float4 *qo[2] = {nullptr, nullptr}, *qd[2] = {nullptr, nullptr};
+    float4* hits = nullptr;
+    float* lsum = nullptr;
+    float4 *st_a = nullptr, *st_b = nullptr, *st_c = nullptr;
+    uint32_t* counters = nullptr; // [0..D] counts, then D+1 trace work counters, then D+1 light work counters
+    int counters_depth = 0;
+    unsigned long long* d_stats = nullptr;
+    int64_t path_bytes = 0;
+
+    // scratch for host-facing calls
+    float* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    void* pinned = nullptr;
+    size_t pinned_bytes = 0;
+
+    int trace_grid = 0, light_grid = 0, shade_grid = 0;
+    bool profiling = false;
+    double ms_trace = 0, ms_light = 0, ms_shade = 0, ms_other = 0, ms_render = 0;
+    uint64_t launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp0 = nullptr, evp1 = nullptr;
+};
+
+namespace {
+
+int fail(ort_ctx* c, const std::string& msg) {
+    if (c) c->err = msg; else g_create_error = msg;
+    return 1;
+}
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(ctx, std::string(#call) + ": " + cudaGetErrorString(e_));                  \
+    } while (0)
+
+struct Bind {
+    int prev = -1;
+    explicit Bind(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~Bind() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+void free_scene(ort_ctx* c) {
+    for (auto t : c->scene_textures) cudaDestroyTextureObject(t);
+    for (auto a : c->scene_arrays) cudaFreeArray(a);
+    for (auto p : c->scene_allocs) cudaFree(p);
+    c->scene_textures.clear(); c->scene_arrays.clear(); c->scene_allocs.clear();
+    c->has_scene = false;
+    c->scene_bytes = 0;
+}
+void free_paths(ort_ctx* c) {
+    void* ptrs[] = {c->qo[0], c->qo[1], c->qd[0], c->qd[1], c->hits, c->lsum, c->st_a, c->st_b, c->st_c};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    c->qo[0] = c->qo[1] = c->qd[0] = c->qd[1] = c->hits = c->st_a = c->st_b = c->st_c = nullptr;
+    c->lsum = nullptr;
+    c->capacity = 0;
+    c->path_bytes = 0;
+}
+
+template <typename T>
+int upload(ort_ctx* ctx, const void* host, size_t count, const T** out) {
+    *out = nullptr;
+    size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    void* d = nullptr;
+    CK(cudaMalloc(&d, bytes));
+    ctx->scene_allocs.push_back(d);
+    ctx->scene_bytes += (int64_t)bytes;
+    if (count) CK(cudaMemcpyAsync(d, host, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    else CK(cudaMemsetAsync(d, 0, bytes, ctx->stream));
+    *out = (const T*)d;
+    return 0;
+}
+
+// texture_index (textures.odin:79-104) applied to every texel on the host: u8 -> /255, missing
+// channels = 1, optional pow(rgb, 2.2); the result is what a point fetch returns on the device.
+int make_texture(ort_ctx* ctx, const ort_texture& t, bool srgb, cudaTextureObject_t* out) {
+    if (t.data == nullptr || t.width <= 0 || t.height <= 0 || t.channels < 1 || t.channels > 4)
+        return fail(ctx, "invalid texture (data/size/channels)");
+    const size_t w = (size_t)t.width, h = (size_t)t.height;
+    std::vector<float> texels(w * h * 4);
+    float lut[256];
+    for (int i = 0; i < 256; i++) {
+        float x = (float)i / 255.0f;
+        lut[i] = srgb ? std::pow(x, 2.2f) : x;
+    }
+    for (size_t y = 0; y < h; y++)
+        for (size_t x = 0; x < w; x++) {
+            float px[4] = {1, 1, 1, 1};
+            const size_t idx = y * (size_t)t.stride + x * (size_t)t.channels;
+            for (int c = 0; c < t.channels; c++) {
+                if (t.is_f32) {
+                    float v = ((const float*)t.data)[idx + c];
+                    px[c] = (srgb && c < 3) ? std::pow(v, 2.2f) : v;
+                } else {
+                    uint8_t v = ((const uint8_t*)t.data)[idx + c];
+                    px[c] = c < 3 ? lut[v] : (float)v / 255.0f;
+                }
+            }
+            if (srgb) // linalg.pow(pixel.rgb, 2.2) also hits the default 1.0 of absent channels: pow(1, 2.2) = 1
+                for (int c = t.channels; c < 3; c++) px[c] = 1.0f;
+            std::memcpy(&texels[(y * w + x) * 4], px, 16);
+        }
+    cudaChannelFormatDesc desc = cudaCreateChannelDesc<float4>();
+    cudaArray_t arr = nullptr;
+    CK(cudaMallocArray(&arr, &desc, w, h));
+    ctx->scene_arrays.push_back(arr);
+    ctx->scene_bytes += (int64_t)(w * h * 16);
+    CK(cudaMemcpy2DToArray(arr, 0, 0, texels.data(), w * 16, w * 16, h, cudaMemcpyHostToDevice));
+    cudaResourceDesc rd{};
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = arr;
+    cudaTextureDesc td{};
+    td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModePoint;
+    td.readMode = cudaReadModeElementType;
+    td.normalizedCoords = 0;
+    cudaTextureObject_t obj = 0;
+    CK(cudaCreateTextureObject(&obj, &rd, &td, nullptr));
+    ctx->scene_textures.push_back(obj);
+    *out = obj;
+    return 0;
+}
+
+int ensure_paths(ort_ctx* ctx, int64_t need) {
+    if (ctx->capacity >= need) return 0;
+    free_paths(ctx);
+    const size_t n = (size_t)need;
+    for (int i = 0; i < 2; i++) {
+        CK(cudaMalloc(&ctx->qo[i], n * 16));
+        CK(cudaMalloc(&ctx->qd[i], n * 16));
+    }
+    CK(cudaMalloc(&ctx->hits, n * 16));
+    CK(cudaMalloc(&ctx->lsum, n * 4));
+    CK(cudaMalloc(&ctx->st_a, n * 16));
+    CK(cudaMalloc(&ctx->st_b, n * 16));
+    CK(cudaMalloc(&ctx->st_c, n * 16));
+    ctx->capacity = need;
+    ctx->path_bytes = (int64_t)(n * (16 * 8 + 4));
+    return 0;
+}
+int ensure_counters(ort_ctx* ctx, int depth) {
+    if (ctx->counters && ctx->counters_depth >= depth) return 0;
+    if (ctx->counters) cudaFree(ctx->counters);
+    ctx->counters = nullptr;
+    CK(cudaMalloc(&ctx->counters, sizeof(uint32_t) * 3 * (size_t)(depth + 2)));
+    ctx->counters_depth = depth;
+    return 0;
+}
+int ensure_scratch(ort_ctx* ctx, size_t bytes) {
+    if (ctx->scratch_bytes >= bytes) return 0;
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    ctx->scratch = nullptr; ctx->scratch_bytes = 0;
+    CK(cudaMalloc(&ctx->scratch, bytes));
+    ctx->scratch_bytes = bytes;
+    return 0;
+}
+int ensure_pinned(ort_ctx* ctx, size_t bytes) {
+    if (ctx->pinned_bytes >= bytes) return 0;
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    ctx->pinned = nullptr; ctx->pinned_bytes = 0;
+    CK(cudaMallocHost(&ctx->pinned, bytes));
+    ctx->pinned_bytes = bytes;
+    return 0;
+}
+
+struct Prof {
+    ort_ctx* c;
+    double* acc;
+    Prof(ort_ctx* ctx, double* a) : c(ctx), acc(a) { if (c->profiling) cudaEventRecord(c->evp0, c->stream); }
+    ~Prof() {
+        if (c->profiling) {
+            cudaEventRecord(c->evp1, c->stream);
+            cudaEventSynchronize(c->evp1);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, c->evp0, c->evp1);
+            *acc += ms;
+        }
+    }
+};
+
+void fill_params(ort_ctx* ctx, uint32_t w, uint32_t h, int32_t depth, RenderParams* p) {
+    float M[16];
+    make_pixel_to_ray_dir(ctx->cam, w, h, M);
+    std::memcpy(p->M, M, sizeof(float) * 12);
+    std::memcpy(p->cam_pos, ctx->cam.pos, 12);
+    p->w = w; p->h = h; p->npix = w * h;
+    p->ray_depth = depth;
+    p->seed = ctx->seed;
+    p->n_batch_samples = 1;
+    p->sample_base = 0;
+}
+
+// One wave: n_batch_samples samples of every pixel, all bounces, then accumulation.
+int launch_wave(ort_ctx* ctx, const RenderParams& p, float* d_accum, float* d_first, float* d_last, int write_first,
+                int write_last) {
+    const int D = p.ray_depth;
+    uint32_t* counts = ctx->counters;
+    uint32_t* wtrace = ctx->counters + (D + 2);
+    uint32_t* wlight = ctx->counters + 2 * (D + 2);
+    cudaStream_t st = ctx->stream;
+    const bool lights = ctx->sd.n_lights > 0;
+    {
+        Prof pr(ctx, &ctx->ms_other);
+        CK(cudaMemsetAsync(ctx->counters, 0, sizeof(uint32_t) * 3 * (size_t)(D + 2), st));
+        k_raygen<<<ctx->shade_grid, 256, 0, st>>>(p, ctx->qo[0], ctx->qd[0], counts);
+        ctx->launches++;
+    }
+    for (int k = 0; k < D; k++) {
+        const int in = k & 1, out = in ^ 1;
+        {
+            Prof pr(ctx, &ctx->ms_trace);
+            k_trace<<<ctx->trace_grid, TRACE_THREADS, 0, st>>>(ctx->sd, ctx->qo[in], ctx->qd[in], counts + k, wtrace + k, ctx->hits);
+            ctx->launches++;
+        }
+        if (k > 0 && lights) {
+            Prof pr(ctx, &ctx->ms_light);
+            k_light<<<ctx->light_grid, TRACE_THREADS, 0, st>>>(ctx->sd, ctx->qo[in], ctx->qd[in], counts + k, wlight + k, ctx->lsum);
+            ctx->launches++;
+        }
+        {
+            Prof pr(ctx, &ctx->ms_shade);
+            k_shade<<<ctx->shade_grid, 256, 0, st>>>(ctx->sd, p, k, ctx->qo[in], ctx->qd[in], ctx->hits, ctx->lsum, counts + k,
+                                                     ctx->qo[out], ctx->qd[out], counts + k + 1, ctx->st_a, ctx->st_b, ctx->st_c);
+            ctx->launches++;
+        }
+    }
+    {
+        Prof pr(ctx, &ctx->ms_other);
+        k_resolve<<<ctx->shade_grid, 256, 0, st>>>(p, ctx->st_c, d_accum, d_first, d_last, write_first, write_last);
+        k_stats<<<1, 32, 0, st>>>(counts, D, lights ? 1 : 0, ctx->d_stats);
+        ctx->launches += 2;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int render_impl(ort_ctx* ctx, uint32_t w, uint32_t h, int32_t depth, uint64_t first_sample, uint64_t n_samples,
+                float* d_accum, float* d_first, float* d_last, const volatile uint8_t* interrupt, uint64_t* done_out) {
+    if (!ctx->has_scene) return fail(ctx, "ort_upload_scene has not been called");
+    if (w == 0 || h == 0) return fail(ctx, "width and height must be non-zero");
+    if (depth < 0) return fail(ctx, "ray_depth must be >= 0");
+    const uint64_t npix = (uint64_t)w * h;
+    if (npix > (1ull << 31)) return fail(ctx, "image too large");
+    int64_t cap = ctx->capacity_cfg > 0 ? ctx->capacity_cfg : ((int64_t)1 << 23);
+    if ((uint64_t)cap < npix) cap = (int64_t)npix;
+    uint64_t per_wave = std::max<uint64_t>(1, (uint64_t)cap / npix);
+    if (per_wave > n_samples) per_wave = std::max<uint64_t>(n_samples, 1);
+    if (ensure_paths(ctx, (int64_t)(per_wave * npix))) return 1;
+    if (ensure_counters(ctx, depth)) return 1;
+    RenderParams p;
+    fill_params(ctx, w, h, depth, &p);
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    uint64_t done = 0;
+    while (done < n_samples) {
+        if (interrupt && *interrupt) break; // is_interrupted(), raytracer.odin:554
+        const uint64_t nb = std::min<uint64_t>(per_wave, n_samples - done);
+        p.sample_base = first_sample + done;
+        p.n_batch_samples = (uint32_t)nb;
+        if (depth == 0) {
+            // raytrace(depth_left = 0) returns 0 (raytracer.odin:433): count the samples, add nothing
+            CK(cudaMemsetAsync(ctx->st_c, 0, (size_t)(nb * npix) * 16, ctx->stream));
+            k_resolve<<<ctx->shade_grid, 256, 0, ctx->stream>>>(p, ctx->st_c, d_accum, d_first, d_last,
+                                                                d_first && done == 0, d_last && done + nb == n_samples);
+            ctx->launches++;
+        } else if (launch_wave(ctx, p, d_accum, d_first, d_last, d_first && done == 0, d_last != nullptr)) {
+            return 1;
+        }
+        done += nb;
+        if (interrupt) CK(cudaStreamSynchronize(ctx->stream)); // keep the poll granular: one wave
+    }
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    if (done_out) *done_out = done;
+    return 0;
+}
+
+} // namespace
+
+// =================================================================================================
+extern "C" {
+
+int ort_abi_version(void) { return ORT_ABI_VERSION; }
+
+const char* ort_last_error(const ort_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int ort_create(ort_ctx** out, const ort_device_cfg* cfg) {
+    ort_ctx* ctx = nullptr; // CK reports into g_create_error while ctx is null
+    if (!out) return fail(nullptr, "ort_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, std::string("no CUDA device: ") + cudaGetErrorString(e) + " (there is no CPU fallback)");
+    const int dev = cfg ? cfg->device : 0;
+    if (dev < 0 || dev >= n) return fail(nullptr, "ort_create: device ordinal out of range");
+    cudaDeviceProp prop{};
+    CK(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10) return fail(nullptr, "ort_create: this library is built for sm_100a (B200) only");
+    Bind b(dev);
+    ort_ctx* c = new ort_ctx();
+    c->device = dev;
+    c->sm_count = prop.multiProcessorCount;
+    c->seed = cfg ? cfg->seed : 0;
+    c->capacity_cfg = cfg ? cfg->max_paths_in_flight : 0;
+    ctx = c;
+    auto bail = [&](const char* what, cudaError_t err) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
+        delete c;
+        return 1;
+    };
+    if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    c->stream = c->own_stream;
+    if ((e = cudaEventCreate(&c->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
+    cudaEventCreate(&c->ev1); cudaEventCreate(&c->evp0); cudaEventCreate(&c->evp1);
+    if ((e = cudaMalloc(&c->d_stats, 8 * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc", e);
+    cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long));
+    // persistent grids: as many CTAs as stay resident, a multiple of the SM count
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace, TRACE_THREADS, 0);
+    c->trace_grid = c->sm_count * std::max(occ, 1);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_light, TRACE_THREADS, 0);
+    c->light_grid = c->sm_count * std::max(occ, 1);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shade, 256, 0);
+    c->shade_grid = c->sm_count * std::max(occ, 1);
+    *out = c;
+    return 0;
+}
+
+void ort_destroy(ort_ctx* ctx) {
+    if (!ctx) return;
+    Bind b(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_scene(ctx);
+    free_paths(ctx);
+    if (ctx->counters) cudaFree(ctx->counters);
+    if (ctx->d_stats) cudaFree(ctx->d_stats);
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->evp0); cudaEventDestroy(ctx->evp1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+int ort_set_stream(ort_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return 1;
+    Bind b(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return 0;
+}
+
+int ort_set_profiling(ort_ctx* ctx, int32_t on) {
+    if (!ctx) return 1;
+    ctx->profiling = on != 0;
+    return 0;
+}
+
+int ort_upload_scene(ort_ctx* ctx, const ort_scene* sc) {
+    if (!ctx) return 1;
+    if (!sc) return fail(ctx, "ort_upload_scene: scene is NULL");
+    Bind b(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    free_scene(ctx);
+    if (sc->n_triangles < 0 || sc->n_light_triangles < 0 || sc->n_materials < 0 || sc->n_textures < 0)
+        return fail(ctx, "ort_upload_scene: negative count");
+    if (sc->n_triangles >= (1 << 28)) return fail(ctx, "ort_upload_scene: more than 2^28 triangles");
+    const char* why = nullptr;
+    if (!build_wide_bvh(sc->bvh, sc->n_bvh_nodes, sc->n_triangles, &ctx->wide, &why))
+        return fail(ctx, std::string("scene BVH: ") + why);
+    if (!build_wide_bvh(sc->light_bvh, sc->n_light_bvh_nodes, sc->n_light_triangles, &ctx->lwide, &why))
+        return fail(ctx, std::string("light BVH: ") + why);
+    if (ctx->wide.max_stack > MAX_STACK || ctx->lwide.max_stack > MAX_STACK)
+        return fail(ctx, "BVH too deep for the traversal stack (worst case " + std::to_string(ctx->wide.max_stack) + " > " +
+                             std::to_string(MAX_STACK) + ")");
+    for (int64_t i = 0; i < sc->n_triangles; i++) {
+        const int64_t m = sc->triangles[i].material_index;
+        if (m < 0 || m >= sc->n_materials) return fail(ctx, "triangle material_index out of range");
+    }
+    ctx->cam = sc->cam;
+    ctx->n_tris = sc->n_triangles;
+    ctx->n_ltris = sc->n_light_triangles;
+    SceneDev sd{};
+    if (upload<float4>(ctx, ctx->wide.nodes.data(), ctx->wide.nodes.size() * 8, &sd.nodes)) return 1;
+    if (upload<float4>(ctx, ctx->lwide.nodes.data(), ctx->lwide.nodes.size() * 8, &sd.lnodes)) return 1;
+    {
+        std::vector<TriIsect> rec((size_t)sc->n_triangles);
+        make_isect_records(sc->triangles, sc->n_triangles, rec.data());
+        if (upload<float4>(ctx, rec.data(), rec.size() * 3, &sd.tris)) return 1;
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    {
+        std::vector<TriIsect> rec((size_t)sc->n_light_triangles);
+        std::vector<TriLight> lrec((size_t)sc->n_light_triangles);
+        make_isect_records(sc->light_triangles, sc->n_light_triangles, rec.data());
+        make_light_records(sc->light_triangles, sc->n_light_triangles, lrec.data());
+        if (upload<float4>(ctx, rec.data(), rec.size() * 3, &sd.ltris)) return 1;
+        if (upload<float4>(ctx, lrec.data(), lrec.size(), &sd.llight)) return 1;
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    bool any_tex = false, any_normal = false;
+    std::vector<DevMaterial> mats((size_t)sc->n_materials);
+    std::vector<char> used_raw((size_t)sc->n_textures, 0), used_lin((size_t)sc->n_textures, 0);
+    for (int64_t i = 0; i < sc->n_materials; i++) {
+        const ort_material& m = sc->materials[i];
+        DevMaterial d{};
+        std::memcpy(d.color, m.color_factor, 12);
+        std::memcpy(d.emission, m.emission_factor, 12);
+        d.roughness = m.roughness_factor;
+        d.metallic = m.metallic_factor;
+        const int32_t ids[4] = {m.color_texture, m.emission_texture, m.metallic_roughness_texture, m.normal_texture};
+        for (int k = 0; k < 4; k++) {
+            if (ids[k] >= sc->n_textures) return fail(ctx, "material texture index out of range");
+            if (ids[k] >= 0) { any_tex = true; (k < 2 ? used_lin : used_raw)[ids[k]] = 1; }
+        }
+        if (m.normal_texture >= 0) any_normal = true;
+        d.color_tex = ids[0] < 0 ? -1 : ids[0]; d.emission_tex = ids[1] < 0 ? -1 : ids[1];
+        d.mr_tex = ids[2] < 0 ? -1 : ids[2]; d.normal_tex = ids[3] < 0 ? -1 : ids[3];
+        mats[(size_t)i] = d;
+    }
+    if (upload<DevMaterial>(ctx, mats.data(), mats.size(), &sd.mats)) return 1;
+    {
+        std::vector<TriShade> rec((size_t)sc->n_triangles);
+        for (int64_t i = 0; i < sc->n_triangles; i++) {
+            const ort_triangle& t = sc->triangles[i];
+            TriShade& r = rec[(size_t)i];
+            std::memcpy(r.n1, t.n1, 12); std::memcpy(r.n2, t.n2, 12); std::memcpy(r.n3, t.n3, 12);
+            r.ngx = t.ng[0]; r.ngy = t.ng[1]; r.ngz = t.ng[2];
+            r.material = (int32_t)t.material_index; r.flags = 0; r.pad0 = r.pad1 = 0;
+        }
+        if (upload<float4>(ctx, rec.data(), rec.size() * 4, &sd.tshade)) return 1;
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    if (any_tex) {
+        std::vector<TriUV> rec((size_t)sc->n_triangles);
+        for (int64_t i = 0; i < sc->n_triangles; i++) {
+            const ort_triangle& t = sc->triangles[i];
+            TriUV& r = rec[(size_t)i];
+            std::memcpy(r.tex1, t.tex1, 8); std::memcpy(r.tex2, t.tex2, 8); std::memcpy(r.tex3, t.tex3, 8);
+            r.pad[0] = r.pad[1] = 0;
+        }
+        if (upload<float4>(ctx, rec.data(), rec.size() * 2, &sd.tuv)) return 1;
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    if (any_normal) {
+        std::vector<TriTan> rec((size_t)sc->n_triangles);
+        for (int64_t i = 0; i < sc->n_triangles; i++) {
+            const ort_triangle& t = sc->triangles[i];
+            std::memcpy(rec[(size_t)i].tan1, t.tan1, 16); std::memcpy(rec[(size_t)i].tan2, t.tan2, 16);
+            std::memcpy(rec[(size_t)i].tan3, t.tan3, 16);
+        }
+        if (upload<float4>(ctx, rec.data(), rec.size() * 3, &sd.ttan)) return 1;
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    {
+        std::vector<DevTexture> texs((size_t)sc->n_textures);
+        for (int64_t i = 0; i < sc->n_textures; i++) {
+            DevTexture d{};
+            d.w = sc->textures[i].width; d.h = sc->textures[i].height;
+            if (used_raw[(size_t)i] && make_texture(ctx, sc->textures[i], false, &d.raw)) return 1;
+            if (used_lin[(size_t)i] && make_texture(ctx, sc->textures[i], true, &d.linear)) return 1;
+            texs[(size_t)i] = d;
+        }
+        if (upload<DevTexture>(ctx, texs.data(), texs.size(), &sd.texs)) return 1;
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    if (sc->env_map) {
+        sd.env.w = sc->env_map->width; sd.env.h = sc->env_map->height;
+        if (make_texture(ctx, *sc->env_map, false, &sd.env.raw)) return 1;
+        sd.has_env = 1;
+    }
+    sd.n_lights = (int32_t)sc->n_light_triangles;
+    std::memcpy(sd.pad_scale, ctx->wide.max_abs, 12);
+    std::memcpy(sd.lpad_scale, ctx->lwide.max_abs, 12);
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->sd = sd;
+    ctx->has_scene = true;
+    return 0;
+}
+
+int ort_render_device(ort_ctx* ctx, uint32_t w, uint32_t h, int32_t ray_depth, uint64_t first_sample,
+                      uint64_t n_samples, float* d_accum) {
+    if (!ctx) return 1;
+    if (!d_accum) return fail(ctx, "ort_render_device: d_accum is NULL");
+    Bind b(ctx->device);
+    return render_impl(ctx, w, h, ray_depth, first_sample, n_samples, d_accum, nullptr, nullptr, nullptr, nullptr);
+}
+
+int ort_render(ort_ctx* ctx, uint32_t w, uint32_t h, int32_t ray_depth, uint64_t first_sample, uint64_t n_samples,
+               ort_sample_stats* out, const volatile uint8_t* interrupt) {
+    if (!ctx) return 1;
+    if (!out) return fail(ctx, "ort_render: out is NULL");
+    Bind b(ctx->device);
+    const size_t npix = (size_t)w * h;
+    // planes: 8 accum + 3 first + 3 last, then the packed Sample_Stats
+    if (ensure_scratch(ctx, npix * (14 * 4 + 52))) return 1;
+    float* accum = ctx->scratch;
+    float* first = accum + 8 * npix;
+    float* last = first + 3 * npix;
+    uint32_t* packed = (uint32_t*)(last + 3 * npix);
+    CK(cudaMemsetAsync(accum, 0, npix * 14 * 4, ctx->stream));
+    uint64_t done = 0;
+    if (render_impl(ctx, w, h, ray_depth, first_sample, n_samples, accum, first, last, interrupt, &done)) return 1;
+    k_pack_stats<<<ctx->shade_grid, 256, 0, ctx->stream>>>(accum, first, last, (uint32_t)npix, packed);
+    ctx->launches++;
+    if (ensure_pinned(ctx, npix * 52)) return 1;
+    CK(cudaMemcpyAsync(ctx->pinned, packed, npix * 52, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->ms_render = ms;
+    // merge like repeated rc_set_pixel calls would (main.odin:96-101)
+    const ort_sample_stats* src = (const ort_sample_stats*)ctx->pinned;
+    for (size_t i = 0; i < npix; i++) {
+        if (src[i].count == 0) continue;
+        ort_sample_stats& d = out[i];
+        if (d.count == 0) std::memcpy(d.first, src[i].first, 12);
+        d.count += src[i].count;
+        std::memcpy(d.last, src[i].last, 12);
+        for (int c = 0; c < 3; c++) { d.total[c] += src[i].total[c]; d.total_squared[c] += src[i].total_squared[c]; }
+    }
+    return 0;
+}
+
+int ort_unpack_accum(ort_ctx* ctx, uint32_t w, uint32_t h, const float* d_accum, ort_sample_stats* out) {
+    if (!ctx) return 1;
+    if (!d_accum || !out) return fail(ctx, "ort_unpack_accum: NULL argument");
+    Bind b(ctx->device);
+    const size_t npix = (size_t)w * h;
+    if (ensure_scratch(ctx, npix * 52)) return 1;
+    k_pack_stats<<<ctx->shade_grid, 256, 0, ctx->stream>>>(d_accum, nullptr, nullptr, (uint32_t)npix, (uint32_t*)ctx->scratch);
+    ctx->launches++;
+    if (ensure_pinned(ctx, npix * 52)) return 1;
+    CK(cudaMemcpyAsync(ctx->pinned, ctx->scratch, npix * 52, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const ort_sample_stats* src = (const ort_sample_stats*)ctx->pinned;
+    for (size_t i = 0; i < npix; i++) {
+        if (src[i].count == 0) continue;
+        ort_sample_stats& d = out[i];
+        const float mean[3] = {src[i].total[0] / (float)src[i].count, src[i].total[1] / (float)src[i].count,
+                               src[i].total[2] / (float)src[i].count};
+        if (d.count == 0) std::memcpy(d.first, mean, 12);
+        d.count += src[i].count;
+        std::memcpy(d.last, mean, 12);
+        for (int c = 0; c < 3; c++) { d.total[c] += src[i].total[c]; d.total_squared[c] += src[i].total_squared[c]; }
+    }
+    return 0;
+}
+
+int ort_trace_rays(ort_ctx* ctx, const ort_ray* rays, int64_t n, ort_hit* out) {
+    if (!ctx) return 1;
+    if (!ctx->has_scene) return fail(ctx, "ort_upload_scene has not been called");
+    if (n < 0 || (n > 0 && (!rays || !out))) return fail(ctx, "ort_trace_rays: bad arguments");
+    Bind b(ctx->device);
+    const int64_t chunk = 1 << 22;
+    if (ensure_paths(ctx, std::min<int64_t>(std::max<int64_t>(n, 1), chunk))) return 1;
+    if (ensure_counters(ctx, 1)) return 1;
+    if (ensure_scratch(ctx, (size_t)std::min<int64_t>(std::max<int64_t>(n, 1), chunk) * 24 * 2)) return 1;
+    for (int64_t off = 0; off < n; off += chunk) {
+        const uint32_t m = (uint32_t)std::min<int64_t>(chunk, n - off);
+        float* d_in = ctx->scratch;
+        float* d_out = ctx->scratch + (size_t)std::min<int64_t>(n, chunk) * 6;
+        CK(cudaMemcpyAsync(d_in, rays + off, (size_t)m * 24, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemsetAsync(ctx->counters, 0, sizeof(uint32_t) * 8, ctx->stream));
+        k_pack_rays<<<ctx->shade_grid, 256, 0, ctx->stream>>>(d_in, m, ctx->qo[0], ctx->qd[0], ctx->counters);
+        k_trace<<<ctx->trace_grid, TRACE_THREADS, 0, ctx->stream>>>(ctx->sd, ctx->qo[0], ctx->qd[0], ctx->counters, ctx->counters + 1, ctx->hits);
+        k_unpack_hits<<<ctx->shade_grid, 256, 0, ctx->stream>>>(ctx->sd, ctx->hits, ctx->qd[0], m, d_out);
+        ctx->launches += 3;
+        CK(cudaMemcpyAsync(out + off, d_out, (size_t)m * 24, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int ort_light_pdf(ort_ctx* ctx, const ort_ray* rays, int64_t n, float* out) {
+    if (!ctx) return 1;
+    if (!ctx->has_scene) return fail(ctx, "ort_upload_scene has not been called");
+    if (n < 0 || (n > 0 && (!rays || !out))) return fail(ctx, "ort_light_pdf: bad arguments");
+    Bind b(ctx->device);
+    if (ctx->sd.n_lights == 0) { std::memset(out, 0, sizeof(float) * (size_t)n); return 0; }
+    const int64_t chunk = 1 << 22;
+    if (ensure_paths(ctx, std::min<int64_t>(std::max<int64_t>(n, 1), chunk))) return 1;
+    if (ensure_counters(ctx, 1)) return 1;
+    if (ensure_scratch(ctx, (size_t)std::min<int64_t>(std::max<int64_t>(n, 1), chunk) * 24)) return 1;
+    for (int64_t off = 0; off < n; off += chunk) {
+        const uint32_t m = (uint32_t)std::min<int64_t>(chunk, n - off);
+        CK(cudaMemcpyAsync(ctx->scratch, rays + off, (size_t)m * 24, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemsetAsync(ctx->counters, 0, sizeof(uint32_t) * 8, ctx->stream));
+        k_pack_rays<<<ctx->shade_grid, 256, 0, ctx->stream>>>(ctx->scratch, m, ctx->qo[0], ctx->qd[0], ctx->counters);
+        k_light<<<ctx->light_grid, TRACE_THREADS, 0, ctx->stream>>>(ctx->sd, ctx->qo[0], ctx->qd[0], ctx->counters, ctx->counters + 1, ctx->lsum);
+        k_scale<<<ctx->shade_grid, 256, 0, ctx->stream>>>(ctx->lsum, m, (float)ctx->sd.n_lights);
+        ctx->launches += 3;
+        CK(cudaMemcpyAsync(out + off, ctx->lsum, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int ort_primary_hits(ort_ctx* ctx, uint32_t w, uint32_t h, uint64_t sample, ort_hit* out, ort_ray* rays_out) {
+    if (!ctx) return 1;
+    if (!ctx->has_scene) return fail(ctx, "ort_upload_scene has not been called");
+    if (!out || w == 0 || h == 0) return fail(ctx, "ort_primary_hits: bad arguments");
+    Bind b(ctx->device);
+    const size_t npix = (size_t)w * h;
+    if (ensure_paths(ctx, (int64_t)npix)) return 1;
+    if (ensure_counters(ctx, 1)) return 1;
+    if (ensure_scratch(ctx, npix * 24)) return 1;
+    RenderParams p;
+    fill_params(ctx, w, h, 1, &p);
+    p.sample_base = sample;
+    p.n_batch_samples = 1;
+    CK(cudaMemsetAsync(ctx->counters, 0, sizeof(uint32_t) * 8, ctx->stream));
+    k_raygen<<<ctx->shade_grid, 256, 0, ctx->stream>>>(p, ctx->qo[0], ctx->qd[0], ctx->counters);
+    k_trace<<<ctx->trace_grid, TRACE_THREADS, 0, ctx->stream>>>(ctx->sd, ctx->qo[0], ctx->qd[0], ctx->counters, ctx->counters + 1, ctx->hits);
+    k_unpack_hits<<<ctx->shade_grid, 256, 0, ctx->stream>>>(ctx->sd, ctx->hits, ctx->qd[0], (uint32_t)npix, ctx->scratch);
+    ctx->launches += 3;
+    CK(cudaMemcpyAsync(out, ctx->scratch, npix * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (rays_out) {
+        k_unpack_rays<<<ctx->shade_grid, 256, 0, ctx->stream>>>(ctx->qo[0], ctx->qd[0], (uint32_t)npix, ctx->scratch);
+        ctx->launches++;
+        CK(cudaMemcpyAsync(rays_out, ctx->scratch, npix * 24, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int ort_tonemap_rgb8(ort_ctx* ctx, uint32_t w, uint32_t h, const float* d_accum, uint8_t* out_rgb) {
+    if (!ctx) return 1;
+    if (!d_accum || !out_rgb) return fail(ctx, "ort_tonemap_rgb8: NULL argument");
+    Bind b(ctx->device);
+    const size_t npix = (size_t)w * h;
+    if (ensure_scratch(ctx, npix * 3)) return 1;
+    k_tonemap<<<ctx->shade_grid, 256, 0, ctx->stream>>>(d_accum, (uint32_t)npix, (uint8_t*)ctx->scratch);
+    ctx->launches++;
+    CK(cudaMemcpyAsync(out_rgb, ctx->scratch, npix * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int ort_get_stats(ort_ctx* ctx, ort_stats* out) {
+    if (!ctx || !out) return 1;
+    Bind b(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    unsigned long long s[8];
+    CK(cudaMemcpy(s, ctx->d_stats, sizeof s, cudaMemcpyDeviceToHost));
+    std::memset(out, 0, sizeof *out);
+    out->rays_closest = s[0]; out->rays_light_pdf = s[1]; out->paths = s[2];
+    out->kernel_launches = ctx->launches;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->ms_render = ms; else cudaGetLastError();
+    out->render_ms = ctx->ms_render;
+    out->trace_ms = ctx->ms_trace; out->light_ms = ctx->ms_light; out->shade_ms = ctx->ms_shade; out->other_ms = ctx->ms_other;
+    out->wide_nodes = (int64_t)ctx->wide.nodes.size();
+    out->wide_depth = ctx->wide.depth;
+    out->light_wide_nodes = (int64_t)ctx->lwide.nodes.size();
+    out->device_bytes = ctx->scene_bytes + ctx->path_bytes;
+    return 0;
+}
+
+int ort_reset_stats(ort_ctx* ctx) {
+    if (!ctx) return 1;
+    Bind b(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemset(ctx->d_stats, 0, 8 * sizeof(unsigned long long)));
+    ctx->ms_trace = ctx->ms_light = ctx->ms_shade = ctx->ms_other = ctx->ms_render = 0;
+    ctx->launches = 0;
+    return 0;
+}
+
+} // extern "C"
