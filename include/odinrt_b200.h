@@ -136,8 +136,12 @@ typedef struct ort_device_cfg {
 } ort_device_cfg;
 
 typedef struct ort_stats {
-    uint64_t rays_closest;   /* cast_ray calls (raytracer.odin:435): primary + continuation */
-    uint64_t rays_light_pdf; /* surface_sampling_pdf traversals (shading.odin:98) */
+    uint64_t rays_closest;   /* cast_ray calls the reference would make (raytracer.odin:435):
+                                primary rays + continuations that pass `norm_l1(value)/pdf > 1e-5` */
+    uint64_t rays_traced;    /* closest-hit traversals actually launched: the continuation ray is
+                                traced together with its light-pdf sum before that test can be
+                                evaluated, so this is >= rays_closest (speculative rays) */
+    uint64_t rays_light_pdf; /* surface_sampling_pdf traversals launched (shading.odin:98) */
     uint64_t paths;          /* pixel-samples completed */
     uint64_t kernel_launches;/* launches of this library's own kernels */
     double   render_ms;      /* device time of the last render call (CUDA events) */

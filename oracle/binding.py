@@ -48,9 +48,9 @@ def load(native=False):
         "orc_bvh_build": (i64, [vp, i64, vp, i64]),
         "orc_check_intersect_ray_aabb": (i32, [pf, pf, pf, pf, f, pf]),
         "orc_intersect_ray_triangle": (None, [pf, pf, vp, pf]),
-        "orc_trace_rays": (None, [vp, vp, i64, i32, vp, C.POINTER(Counters), i32]),
+        "orc_trace_rays": (None, [vp, vp, i64, i32, vp, C.POINTER(Counters), i32, vp]),
         "orc_light_pdf": (None, [vp, vp, i64, vp]),
-        "orc_primary_hits": (None, [vp, u32, u32, u64, u64, i32, vp, vp, C.POINTER(Counters), i32]),
+        "orc_primary_hits": (None, [vp, u32, u32, u64, u64, i32, vp, vp, C.POINTER(Counters), i32, vp]),
         "orc_render": (None, [vp, u32, u32, C.c_int32, u64, u64, u64, i32, i32, i32, u32, u32, u32, u32, vp,
                               C.POINTER(Counters)]),
         "orc_shade": (None, [pf, pf, f, f, pf, pf, pf]),
@@ -106,7 +106,9 @@ class OracleScene:
         rays = np.ascontiguousarray(rays, cabi.RAY_DTYPE)
         out = np.zeros(len(rays), cabi.HIT_DTYPE)
         c = Counters()
-        self.lib.orc_trace_rays(self.ref, rays.ctypes.data, len(rays), mode, out.ctypes.data, C.byref(c), threads)
+        self.ties = np.zeros(len(rays), np.uint8)  # 1 = result depends on visiting order (exact-t tie)
+        self.lib.orc_trace_rays(self.ref, rays.ctypes.data, len(rays), mode, out.ctypes.data, C.byref(c), threads,
+                                self.ties.ctypes.data)
         return out, c.as_dict()
 
     def light_pdf(self, rays):
@@ -123,8 +125,9 @@ class OracleScene:
         out = np.zeros(w * h, cabi.HIT_DTYPE)
         rays = np.zeros(w * h, cabi.RAY_DTYPE)
         c = Counters()
+        self.ties = np.zeros(w * h, np.uint8)
         self.lib.orc_primary_hits(self.ref, w, h, sample, seed, mode, out.ctypes.data, rays.ctypes.data,
-                                  C.byref(c), threads)
+                                  C.byref(c), threads, self.ties.ctypes.data)
         return out, rays, c.as_dict()
 
     def render(self, w, h, ray_depth, n_samples, first_sample=0, seed=0, mode=0, schedule=1, threads=8,

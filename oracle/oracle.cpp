@@ -276,6 +276,7 @@ struct Hit {
 struct Counters {
     uint64_t rays, node_pops, box_tests, tri_tests, stack_drops, stack_high, exact_ties;
     uint64_t light_rays, light_node_pops, light_box_tests, light_tri_tests;
+    float last_tie_t; // instrumentation: t of the most recent exact tie of the current ray (NaN = none)
 };
 
 struct SceneView {
@@ -295,7 +296,10 @@ inline Hit cast_ray_through_trigs(const ort_triangle* trigs, int64_t first, int6
         if (c) {
             c->tri_tests++;
             int64_t cur_best = hit.trig >= 0 ? hit.trig : best_trig;
-            if (gh.t > 0 && gh.t == hit.t && cur_best >= 0 && cur_best != first + i) c->exact_ties++;
+            if (gh.t > 0 && gh.t == hit.t && cur_best >= 0 && cur_best != first + i) {
+                c->exact_ties++;
+                c->last_tie_t = gh.t;
+            }
         }
         if (gh.t > 0 && gh.t < hit.t) hit = {first + i, gh.t, gh.inside, gh.u, gh.v}; // :360
     }
@@ -800,8 +804,10 @@ void orc_intersect_ray_triangle(const float o[3], const float d[3], const ort_tr
 }
 
 // cast_ray on n rays; mode 0 faithful / 1 ideal.
+// ties_out (may be NULL): 1 where a DIFFERENT triangle produced a t bit-identical to the winner's,
+// i.e. where the result depends on the visiting order (SURVEY.md §7 "exact-t ties").
 void orc_trace_rays(const ort_scene* scene, const ort_ray* rays, int64_t n, int mode, ort_hit* out,
-                    orc_counters* counters, int threads) {
+                    orc_counters* counters, int threads, uint8_t* ties_out) {
     SceneView sv{scene, mode};
     if (threads < 1) threads = 1;
     std::vector<Counters> cs((size_t)threads);
@@ -810,7 +816,9 @@ void orc_trace_rays(const ort_scene* scene, const ort_ray* rays, int64_t n, int 
         Counters c{};
         for (int64_t i = tid; i < n; i += threads) {
             Ray r = {v3(rays[i].o), v3(rays[i].d)};
+            c.last_tie_t = std::numeric_limits<float>::quiet_NaN();
             Hit h = cast_ray(sv, r, INF_F32, &c);
+            if (ties_out) ties_out[i] = (h.trig >= 0 && c.last_tie_t + RAY_EPS == h.t) ? 1 : 0;
             out[i].t = h.t; out[i].u = h.u; out[i].v = h.v;
             out[i].tri = (int32_t)h.trig;
             out[i].material = h.trig < 0 ? -1 : (int32_t)scene->triangles[h.trig].material_index;
@@ -833,7 +841,7 @@ void orc_light_pdf(const ort_scene* scene, const ort_ray* rays, int64_t n, float
 
 // Primary rays + their cast_ray result for one sample index; pixel order y*w + x (unflipped).
 void orc_primary_hits(const ort_scene* scene, uint32_t w, uint32_t h, uint64_t sample, uint64_t seed, int mode,
-                      ort_hit* out, ort_ray* rays_out, orc_counters* counters, int threads) {
+                      ort_hit* out, ort_ray* rays_out, orc_counters* counters, int threads, uint8_t* ties_out) {
     SceneView sv{scene, mode};
     M4 M = pixel_to_ray_dir(scene->cam, w, h);
     if (threads < 1) threads = 1;
@@ -850,7 +858,9 @@ void orc_primary_hits(const ort_scene* scene, uint32_t w, uint32_t h, uint64_t s
                     rays_out[i].o[0] = r.o.x; rays_out[i].o[1] = r.o.y; rays_out[i].o[2] = r.o.z;
                     rays_out[i].d[0] = r.d.x; rays_out[i].d[1] = r.d.y; rays_out[i].d[2] = r.d.z;
                 }
+                c.last_tie_t = std::numeric_limits<float>::quiet_NaN();
                 Hit hh = cast_ray(sv, r, INF_F32, &c);
+                if (ties_out) ties_out[i] = (hh.trig >= 0 && c.last_tie_t + RAY_EPS == hh.t) ? 1 : 0;
                 out[i].t = hh.t; out[i].u = hh.u; out[i].v = hh.v;
                 out[i].tri = (int32_t)hh.trig;
                 out[i].material = hh.trig < 0 ? -1 : (int32_t)scene->triangles[hh.trig].material_index;

@@ -80,7 +80,7 @@ class OrtDeviceCfg(C.Structure):
 
 class OrtStats(C.Structure):
     _fields_ = [
-        ("rays_closest", C.c_uint64), ("rays_light_pdf", C.c_uint64), ("paths", C.c_uint64),
+        ("rays_closest", C.c_uint64), ("rays_traced", C.c_uint64), ("rays_light_pdf", C.c_uint64), ("paths", C.c_uint64),
         ("kernel_launches", C.c_uint64),
         ("render_ms", C.c_double), ("trace_ms", C.c_double), ("light_ms", C.c_double),
         ("shade_ms", C.c_double), ("other_ms", C.c_double),

@@ -498,14 +498,14 @@ __global__ void __launch_bounds__(256)
 k_shade(const SceneDev s, const RenderParams p, const int bounce, const float4* __restrict__ qo_in,
         const float4* __restrict__ qd_in, const float4* __restrict__ hits, const float* __restrict__ lsum,
         const uint32_t* __restrict__ n_in_ptr, float4* __restrict__ qo_out, float4* __restrict__ qd_out,
-        uint32_t* __restrict__ n_out_ptr, float4* __restrict__ st_a, float4* __restrict__ st_b,
-        float4* __restrict__ st_c) {
+        uint32_t* __restrict__ n_out_ptr, uint32_t* __restrict__ used_ptr, float4* __restrict__ st_a,
+        float4* __restrict__ st_b, float4* __restrict__ st_c) {
     const uint32_t n_in = *n_in_ptr;
     const int lane = threadIdx.x & 31;
     const bool has_lights = s.n_lights > 0;
     for (uint32_t base = blockIdx.x * blockDim.x; base < n_in; base += gridDim.x * blockDim.x) {
         const uint32_t pos = base + threadIdx.x;
-        bool emit = false;
+        bool emit = false, used = false;
         float4 out_o = make_float4(0, 0, 0, 0), out_d = make_float4(0, 0, 0, 0);
         if (pos < n_in) {
             const float4 o4 = qo_in[pos];
@@ -525,6 +525,7 @@ k_shade(const SceneDev s, const RenderParams p, const int bounce, const float4* 
                 if (norm_l1(value) / pdf > 1e-5f) T = mk3(a.x, a.y, a.z) * value / pdf;
                 else alive = false; // exitance = emission only: L already holds it
             }
+            used = alive; // this traversal is a cast_ray call the reference makes (raytracer.odin:496)
             if (alive) {
                 const int tri = __float_as_int(h4.w);
                 if (tri < 0) {
@@ -639,6 +640,8 @@ k_shade(const SceneDev s, const RenderParams p, const int bounce, const float4* 
                 }
             }
         }
+        const unsigned umask = __ballot_sync(0xffffffffu, used);
+        if (umask && lane == 0) atomicAdd(used_ptr, (uint32_t)__popc(umask));
         // queue compaction: warp ballot + prefix popcount + one atomic per warp
         const unsigned mask = __ballot_sync(0xffffffffu, emit);
         if (mask) {
@@ -682,18 +685,21 @@ __global__ void k_resolve(const RenderParams p, const float4* __restrict__ st_c,
     }
 }
 
-// counters: [0 .. D] queue sizes per bounce.  stats: [0] closest rays, [1] light rays, [2] paths
-__global__ void k_stats(const uint32_t* __restrict__ counts, const int depth, const int has_lights,
-                        unsigned long long* __restrict__ stats) {
+// counters: [0 .. D] queue sizes per bounce; used[k]: traversals of bounce k whose result counted.
+// stats: [0] reference-equivalent closest rays  [1] light rays  [2] paths  [3] traversals launched
+__global__ void k_stats(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ used, const int depth,
+                        const int has_lights, unsigned long long* __restrict__ stats) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
-        unsigned long long rays = 0, lrays = 0;
+        unsigned long long rays = 0, lrays = 0, traced = 0;
         for (int k = 0; k < depth; k++) {
-            rays += counts[k];
+            rays += used[k];
+            traced += counts[k];
             if (k > 0 && has_lights) lrays += counts[k];
         }
         stats[0] += rays;
         stats[1] += lrays;
         stats[2] += counts[0];
+        stats[3] += traced;
     }
 }
 

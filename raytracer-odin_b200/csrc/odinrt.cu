@@ -45,7 +45,7 @@ struct ort_ctx {
     float4* hits = nullptr;
     float* lsum = nullptr;
     float4 *st_a = nullptr, *st_b = nullptr, *st_c = nullptr;
-    uint32_t* counters = nullptr; // [0..D] counts, then D+1 trace work counters, then D+1 light work counters
+    uint32_t* counters = nullptr; // 4 arrays of D+2: queue counts, trace work counters, light work counters, used-ray counts
     int counters_depth = 0;
     unsigned long long* d_stats = nullptr;
     int64_t path_bytes = 0;
@@ -184,7 +184,7 @@ int ensure_counters(ort_ctx* ctx, int depth) {
     if (ctx->counters && ctx->counters_depth >= depth) return 0;
     if (ctx->counters) cudaFree(ctx->counters);
     ctx->counters = nullptr;
-    CK(cudaMalloc(&ctx->counters, sizeof(uint32_t) * 3 * (size_t)(depth + 2)));
+    CK(cudaMalloc(&ctx->counters, sizeof(uint32_t) * 4 * (size_t)(depth + 2)));
     ctx->counters_depth = depth;
     return 0;
 }
@@ -239,11 +239,12 @@ int launch_wave(ort_ctx* ctx, const RenderParams& p, float* d_accum, float* d_fi
     uint32_t* counts = ctx->counters;
     uint32_t* wtrace = ctx->counters + (D + 2);
     uint32_t* wlight = ctx->counters + 2 * (D + 2);
+    uint32_t* used = ctx->counters + 3 * (D + 2);
     cudaStream_t st = ctx->stream;
     const bool lights = ctx->sd.n_lights > 0;
     {
         Prof pr(ctx, &ctx->ms_other);
-        CK(cudaMemsetAsync(ctx->counters, 0, sizeof(uint32_t) * 3 * (size_t)(D + 2), st));
+        CK(cudaMemsetAsync(ctx->counters, 0, sizeof(uint32_t) * 4 * (size_t)(D + 2), st));
         k_raygen<<<ctx->shade_grid, 256, 0, st>>>(p, ctx->qo[0], ctx->qd[0], counts);
         ctx->launches++;
     }
@@ -262,14 +263,14 @@ int launch_wave(ort_ctx* ctx, const RenderParams& p, float* d_accum, float* d_fi
         {
             Prof pr(ctx, &ctx->ms_shade);
             k_shade<<<ctx->shade_grid, 256, 0, st>>>(ctx->sd, p, k, ctx->qo[in], ctx->qd[in], ctx->hits, ctx->lsum, counts + k,
-                                                     ctx->qo[out], ctx->qd[out], counts + k + 1, ctx->st_a, ctx->st_b, ctx->st_c);
+                                                     ctx->qo[out], ctx->qd[out], counts + k + 1, used + k, ctx->st_a, ctx->st_b, ctx->st_c);
             ctx->launches++;
         }
     }
     {
         Prof pr(ctx, &ctx->ms_other);
         k_resolve<<<ctx->shade_grid, 256, 0, st>>>(p, ctx->st_c, d_accum, d_first, d_last, write_first, write_last);
-        k_stats<<<1, 32, 0, st>>>(counts, D, lights ? 1 : 0, ctx->d_stats);
+        k_stats<<<1, 32, 0, st>>>(counts, used, D, lights ? 1 : 0, ctx->d_stats);
         ctx->launches += 2;
     }
     CK(cudaGetLastError());
@@ -688,7 +689,7 @@ int ort_get_stats(ort_ctx* ctx, ort_stats* out) {
     unsigned long long s[8];
     CK(cudaMemcpy(s, ctx->d_stats, sizeof s, cudaMemcpyDeviceToHost));
     std::memset(out, 0, sizeof *out);
-    out->rays_closest = s[0]; out->rays_light_pdf = s[1]; out->paths = s[2];
+    out->rays_closest = s[0]; out->rays_light_pdf = s[1]; out->paths = s[2]; out->rays_traced = s[3];
     out->kernel_launches = ctx->launches;
     float ms = 0;
     if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->ms_render = ms; else cudaGetLastError();

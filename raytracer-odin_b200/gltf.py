@@ -136,7 +136,7 @@ def read_gltf(gltf_path: str) -> Scene:
     j = g.j
     scene = Scene()
     tris: List[np.ndarray] = []
-    mats: List[tuple] = [tuple(np.zeros(1, cabi.MAT_DTYPE)[0])]  # dummy material 0
+    mats: List[tuple] = [((0, 0, 0), -1, (0, 0, 0), -1, 0.0, 0.0, -1, -1)]  # dummy Material{} 0: nil samplers
     texture_cache: Dict[str, int] = {}
     textures: List[np.ndarray] = []
 

@@ -18,7 +18,8 @@ class Scene:
     # scene.trigs[1:] — the dummy triangle 0 (input.odin:43) is never stored
     triangles: np.ndarray = field(default_factory=lambda: np.zeros(0, cabi.TRI_DTYPE))
     # scene.materials INCLUDING the dummy material 0 (input.odin:44)
-    materials: np.ndarray = field(default_factory=lambda: np.zeros(1, cabi.MAT_DTYPE))
+    materials: np.ndarray = field(default_factory=lambda: np.array(
+        [((0, 0, 0), -1, (0, 0, 0), -1, 0.0, 0.0, -1, -1)], cabi.MAT_DTYPE))
     textures: List[np.ndarray] = field(default_factory=list)  # HxWxC uint8 or float32, C in 1..4
     env_map: Optional[np.ndarray] = None
     # filled by finish()

@@ -276,10 +276,10 @@ def cornell(path: str) -> str:
     # light just below the ceiling (not coplanar: no exact-t ties with the ceiling quad)
     add(quad((-0.25, 0.995, 0.25), (-0.25, 0.995, -0.25), (0.25, 0.995, -0.25), (0.25, 0.995, 0.25)), light)
     pos, idx = box((-0.3, -0.6, -0.3), (0.3, 0.6, 0.3))
-    w.node(mesh=w.mesh(w.geometry(pos, idx), white), translation=(-0.35, -0.4, -0.3),
+    w.node(mesh=w.mesh(w.geometry(pos, idx), white), translation=(-0.35, -0.397, -0.3),  # 3 mm above the floor: no coplanar faces
            rotation=quat_from_axis_angle((0, 1, 0), 0.3))
     pos, idx = box((-0.3, -0.3, -0.3), (0.3, 0.3, 0.3))
-    w.node(mesh=w.mesh(w.geometry(pos, idx), glossy), translation=(0.35, -0.7, 0.3),
+    w.node(mesh=w.mesh(w.geometry(pos, idx), glossy), translation=(0.35, -0.697, 0.3),
            rotation=quat_from_axis_angle((0, 1, 0), -0.3))
     w.camera_look_at((0, 0, 3.9), (0, 0, 0), yfov=0.69)
     return w.save(path)

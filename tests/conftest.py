@@ -60,6 +60,7 @@ def scenes(scene_dir):
             p = scenegen.spheres(os.path.join(d, "s.gltf"), n_spheres=14, subdiv=2, seed=5)
         elif name == "spheres_nolight":
             p = scenegen.spheres(os.path.join(d, "s.gltf"), n_spheres=10, subdiv=1, seed=9, n_emissive=0)
+            env = scenegen.write_env_hdr(os.path.join(d, "env.hdr"), 64, 32, sun_peak=50.0)
         elif name == "spheres_c2":
             p = scenegen.spheres(os.path.join(d, "s.gltf"))
         elif name == "terrain_small":
