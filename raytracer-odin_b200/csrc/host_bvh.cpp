@@ -34,8 +34,10 @@ struct Ent {
 
 inline void box_grow(Box& a, const Box& b) {
     for (int k = 0; k < 3; k++) {
-        a.lo[k] = b.lo[k] < a.lo[k] ? b.lo[k] : a.lo[k]; // linalg.min(lhs, rhs): rhs wins only if smaller
-        a.hi[k] = b.hi[k] > a.hi[k] ? b.hi[k] : a.hi[k];
+        // aabb_merge(lhs = a, rhs = b) with Odin's min/max = select(l < r, l, r) / select(l > r, l, r):
+        // on equal-comparing values (+0 / -0) the RIGHT operand is kept, bit for bit
+        a.lo[k] = a.lo[k] < b.lo[k] ? a.lo[k] : b.lo[k];
+        a.hi[k] = a.hi[k] > b.hi[k] ? a.hi[k] : b.hi[k];
     }
 }
 inline Box box_empty() { return {{kInf, kInf, kInf}, {-kInf, -kInf, -kInf}}; }
@@ -335,8 +337,9 @@ extern "C" int64_t ort_bvh_build(ort_triangle* tris, int64_t n, ort_bvh_node* no
         for (int k = 0; k < 3; k++) { // aabb_of_triangle raytracer.odin:197: p, p+u, p+v
             float p0 = t.p[k], p1 = t.p[k] + t.u[k], p2 = t.p[k] + t.v[k];
             float lo = p0, hi = p0;
-            lo = p1 < lo ? p1 : lo; hi = p1 > hi ? p1 : hi;
-            lo = p2 < lo ? p2 : lo; hi = p2 > hi ? p2 : hi;
+            lo = lo < p0 ? lo : p0; hi = hi > p0 ? hi : p0; // aabb_of_points merges points[0] too
+            lo = lo < p1 ? lo : p1; hi = hi > p1 ? hi : p1;
+            lo = lo < p2 ? lo : p2; hi = hi > p2 ? hi : p2;
             b.lo[k] = lo; b.hi[k] = hi;
         }
         ent[i].box = b;
