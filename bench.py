@@ -226,7 +226,8 @@ def main():
 
     r = api.Renderer(device=local, seed=SEED)
     r.upload_scene(scene)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()  # explicit stream: the library, the events and NCCL all order on it
+    torch.cuda.set_stream(stream)
     r.set_stream(stream.cuda_stream)
     accum = torch.zeros(8, npix, device="cuda", dtype=torch.float32)
 
@@ -266,7 +267,7 @@ def main():
     value = rays / (ms * 1e-3) / 1e6
 
     # ---- e2e: public host call, HOST buffers, scene H2D + Sample_Stats D2H inside the timed region
-    r.set_stream(0)
+    r.set_stream(None)
     cs, keep = scene.to_c()
     h2d = (scene.triangles.nbytes + scene.bvh.nbytes + scene.light_triangles.nbytes + scene.light_bvh.nbytes +
            scene.materials.nbytes + sum(t_.nbytes for t_ in scene.textures) +

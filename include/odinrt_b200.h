@@ -167,7 +167,9 @@ void ort_destroy(ort_ctx* ctx);
 const char* ort_last_error(const ort_ctx* ctx); /* ctx may be NULL: last error of ort_create */
 
 /* Run all subsequent work of this context on an externally owned cudaStream_t (e.g. torch's
- * current stream). NULL = the context's own stream. */
+ * current stream).  The handle is used as given — 0 is CUDA's legacy default stream — and
+ * ORT_OWN_STREAM returns to the context's own non-blocking stream. */
+#define ORT_OWN_STREAM ((void*)(intptr_t)-1)
 int  ort_set_stream(ort_ctx* ctx, void* cuda_stream);
 
 /* Deep-copies the scene to the device: re-emits the reference BVHs (scene + light) as flattened

@@ -63,8 +63,11 @@ class Renderer:
         self.scene = scene
         return self
 
-    def set_stream(self, cuda_stream: int):
-        self._check(self.lib.ort_set_stream(self._ctx, C.c_void_p(cuda_stream)))
+    def set_stream(self, cuda_stream):
+        """cuda_stream: a cudaStream_t handle as int (0 = legacy default stream, e.g.
+        torch.cuda.current_stream().cuda_stream), or None for the context's own stream."""
+        h = C.c_void_p(-1) if cuda_stream is None else C.c_void_p(cuda_stream)
+        self._check(self.lib.ort_set_stream(self._ctx, h))
 
     def set_profiling(self, on: bool):
         self._check(self.lib.ort_set_profiling(self._ctx, 1 if on else 0))

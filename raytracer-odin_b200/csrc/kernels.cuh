@@ -1,9 +1,9 @@
 // kernels.cuh — the wavefront path-tracing kernels (sm_100a).
 //
 //   k_raygen      render_task's inner loop head (raytracer.odin:580-586): jittered pinhole rays
-//   k_trace       cast_ray (raytracer.odin:416-430) on the 4-wide re-emission of the reference
-//                 BVH: persistent warps, shared-memory traversal stack, 16-byte node/triangle loads
-//   k_light       surface_sampling_pdf_bvh_sum (shading.odin:62-94): all-hit sum over the light BVH
+//   k_trace       (traverse.cuh) cast_ray (raytracer.odin:416-430) on the 4-wide re-emission of the
+//                 reference BVH fused with surface_sampling_pdf_bvh_sum (shading.odin:62-94) on the
+//                 light BVH: persistent warps, phase voting, per-lane dynamic fetch
 //   k_shade       raytrace's body (raytracer.odin:437-500) + sample/pdf/shade (shading.odin),
 //                 texture fetches through texture objects, ballot/prefix-sum queue compaction
 //   k_resolve     rc_set_pixel (main.odin:89-102): per-pixel accumulation in sample order
@@ -19,8 +19,8 @@ constexpr float PI_F = 3.14159265358979323846264338327950288f;
 constexpr float TAU_F = 6.28318530717958647692528676655900576f;
 
 constexpr int TRACE_THREADS = 128;
-constexpr int SMEM_STACK = 12;   // stack entries per thread kept in shared memory
-constexpr int LOCAL_STACK = 116; // overflow entries per thread in local memory
+constexpr int SMEM_STACK = 16;   // stack entries per thread kept in shared memory
+constexpr int LOCAL_STACK = 112; // overflow entries per thread in local memory
 constexpr int MAX_STACK = SMEM_STACK + LOCAL_STACK;
 
 struct DevMaterial {
@@ -36,11 +36,12 @@ struct DevTexture {
 };
 
 struct SceneDev {
-    const float4* nodes;  // WideNode[], 8 float4 each
-    const float4* tris;   // TriIsect[], 3 float4 each
-    const float4* lnodes; // light BVH
-    const float4* ltris;  // light TriIsect[]
-    const float4* llight; // TriLight[]
+    const float4* nodes;  // WideNode[], 8 float4 each: scene BVH (root 0) followed by the light BVH
+    const float4* tris;   // TriIsect[], 3 float4 each: scene triangles followed by the light triangles
+    const float4* ltris;  // = tris + 3 * light_tri_base (light sampling, shading.odin:41-50)
+    const float4* llight; // TriLight[], indexed by light triangle
+    int32_t light_root;       // node index of the light BVH root inside `nodes`
+    uint32_t light_tri_base;  // index of the first light triangle inside `tris`
     const float4* tshade; // TriShade[], 4 float4 each
     const float4* tuv;    // TriUV[], 2 float4 each
     const float4* ttan;   // TriTan[], 3 float4 each
@@ -49,8 +50,7 @@ struct SceneDev {
     DevTexture env;
     int32_t has_env;
     int32_t n_lights;
-    float pad_scale[3];  // max |coordinate| of the scene root box
-    float lpad_scale[3]; // same for the light BVH
+    float pad_scale[3];  // max |coordinate| of the scene root box (light triangles are scene triangles)
 };
 
 struct RenderParams {
@@ -139,218 +139,9 @@ __device__ __forceinline__ bool tri_uv(const RaySetup& r, float4 a, float4 b, fl
     return !(u < 0.0f || v < 0.0f || addr(u, v) > 1.0f);
 }
 
-struct Stack {
-    int* s_node;   // shared: [SMEM_STACK][TRACE_THREADS]
-    float* s_dist;
-    int l_node[LOCAL_STACK];
-    float l_dist[LOCAL_STACK];
-    int sp;
-    __device__ __forceinline__ void push(int node, float dist) {
-        if (sp < SMEM_STACK) {
-            s_node[sp * TRACE_THREADS] = node;
-            s_dist[sp * TRACE_THREADS] = dist;
-        } else {
-            l_node[sp - SMEM_STACK] = node;
-            l_dist[sp - SMEM_STACK] = dist;
-        }
-        sp++;
-    }
-    __device__ __forceinline__ void pop(int& node, float& dist) {
-        sp--;
-        if (sp < SMEM_STACK) {
-            node = s_node[sp * TRACE_THREADS];
-            dist = s_dist[sp * TRACE_THREADS];
-        } else {
-            node = l_node[sp - SMEM_STACK];
-            dist = l_dist[sp - SMEM_STACK];
-        }
-    }
-};
-
-#define ORT_CSWAP(da, ca, db, cb)            \
-    {                                        \
-        bool sw_ = db < da;                  \
-        float td_ = sw_ ? db : da;           \
-        int tc_ = sw_ ? cb : ca;             \
-        db = sw_ ? da : db; cb = sw_ ? ca : cb; \
-        da = td_; ca = tc_;                  \
-    }
-
-// ------------------------------------------------------------------------------------------------
-// k_trace: closest hit (cast_ray, raytracer.odin:416).  Persistent warps pull 32-ray packets from
-// the compacted queue with one atomic per packet.  hits[pos] = (t without the trailing +RAY_EPS,
-// u, v, triangle id as int bits; -1 = miss).
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TRACE_THREADS)
-k_trace(const SceneDev s, const float4* __restrict__ qo, const float4* __restrict__ qd,
-        const uint32_t* __restrict__ n_ptr, uint32_t* __restrict__ work_ctr, float4* __restrict__ hits) {
-    __shared__ int sh_node[SMEM_STACK * TRACE_THREADS];
-    __shared__ float sh_dist[SMEM_STACK * TRACE_THREADS];
-    const uint32_t n = *n_ptr;
-    const int lane = threadIdx.x & 31;
-    Stack st;
-    st.s_node = sh_node + threadIdx.x;
-    st.s_dist = sh_dist + threadIdx.x;
-    const float best_pad = 1.0f + 7.62939453125e-06f; // 1 + 2^-17: distance culling margin
-
-    for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(work_ctr, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        const uint32_t pos = base + lane;
-        if (pos < n) {
-            const RaySetup r = make_ray(ldg4(qo + pos), ldg4(qd + pos), s.pad_scale);
-            float best = __int_as_float(0x7f800000); // max_dist = +inf (raytracer.odin:435)
-            float hu = 0.0f, hv = 0.0f;
-            int htri = -1;
-            st.sp = 0;
-            int cur = 0; // root
-            for (;;) {
-                while (cur >= 0) {
-                    const float4* nd = s.nodes + (size_t)cur * 8;
-                    const float4 nxp = ldg4(nd + r.sx), fxp = ldg4(nd + (r.sx ^ 1));
-                    const float4 nyp = ldg4(nd + r.sy), fyp = ldg4(nd + (r.sy ^ 1));
-                    const float4 nzp = ldg4(nd + r.sz), fzp = ldg4(nd + (r.sz ^ 1));
-                    const int4 ch = __ldg(reinterpret_cast<const int4*>(nd + 6));
-                    const float lim = best * best_pad;
-                    float d0, d1, d2, d3;
-                    int c0 = ch.x, c1 = ch.y, c2 = ch.z, c3 = ch.w;
-#define ORT_BOX(k, D, C)                                                                          \
-    {                                                                                             \
-        float tn = fmaxf(fmaxf(fmaf(nxp.k, r.ix, r.nx), fmaf(nyp.k, r.iy, r.ny)),                 \
-                         fmaxf(fmaf(nzp.k, r.iz, r.nz), 0.0f));                                   \
-        float tf = fminf(fminf(fmaf(fxp.k, r.ix, r.fx), fmaf(fyp.k, r.iy, r.fy)),                 \
-                         fminf(fmaf(fzp.k, r.iz, r.fz), lim));                                    \
-        D = (tn <= tf && C != WIDE_EMPTY) ? tn : __int_as_float(0x7f800000);                      \
-    }
-                    ORT_BOX(x, d0, c0) ORT_BOX(y, d1, c1) ORT_BOX(z, d2, c2) ORT_BOX(w, d3, c3)
-#undef ORT_BOX
-                    const float inf = __int_as_float(0x7f800000);
-                    const int nh = (d0 < inf) + (d1 < inf) + (d2 < inf) + (d3 < inf);
-                    ORT_CSWAP(d0, c0, d1, c1) ORT_CSWAP(d2, c2, d3, c3) ORT_CSWAP(d0, c0, d2, c2)
-                    ORT_CSWAP(d1, c1, d3, c3) ORT_CSWAP(d1, c1, d2, c2)
-                    if (nh == 0) {
-                        // pop, skipping entries the current best already culls
-                        cur = WIDE_EMPTY;
-                        while (st.sp > 0) {
-                            int nd2; float dd;
-                            st.pop(nd2, dd);
-                            if (dd <= best * best_pad) { cur = nd2; break; }
-                        }
-                    } else {
-                        if (nh > 3) st.push(c3, d3);
-                        if (nh > 2) st.push(c2, d2);
-                        if (nh > 1) st.push(c1, d1);
-                        cur = c0;
-                    }
-                }
-                if (cur == WIDE_EMPTY) break;
-                // leaf: cast_ray_through_trigs (raytracer.odin:351-369), reference order, first wins ties
-                {
-                    const uint32_t code = (uint32_t)~cur;
-                    const uint32_t first = code >> 3, cnt = code & 7u;
-                    for (uint32_t i = 0; i < cnt; i++) {
-                        const float4* tp = s.tris + (size_t)(first + i) * 3;
-                        const float4 a = ldg4(tp), b = ldg4(tp + 1), c = ldg4(tp + 2);
-                        float id, bx, by, bz, t, a00, a10;
-                        tri_det_t(r, a, b, c, id, bx, by, bz, t, a00, a10);
-                        if (t > 0.0f && t < best) { // raytracer.odin:360
-                            float u, v;
-                            if (tri_uv(r, a, b, c, id, bx, by, bz, a00, a10, u, v)) {
-                                best = t; hu = u; hv = v; htri = (int)(first + i);
-                            }
-                        }
-                    }
-                }
-                cur = WIDE_EMPTY;
-                while (st.sp > 0) {
-                    int nd2; float dd;
-                    st.pop(nd2, dd);
-                    if (dd <= best * best_pad) { cur = nd2; break; }
-                }
-                if (cur == WIDE_EMPTY) break;
-            }
-            hits[pos] = make_float4(htri >= 0 ? best : 0.0f, hu, hv, __int_as_float(htri));
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// k_light: surface_sampling_pdf_bvh_sum (shading.odin:62-94) — every light triangle the
-// unbounded ray hits with t >= 0 contributes (2/|u x v|) * t^2 / |ng.d|.  lsum[pos] = the sum
-// (the division by the light count, shading.odin:99, happens in k_shade).
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TRACE_THREADS)
-k_light(const SceneDev s, const float4* __restrict__ qo, const float4* __restrict__ qd,
-        const uint32_t* __restrict__ n_ptr, uint32_t* __restrict__ work_ctr, float* __restrict__ lsum) {
-    __shared__ int sh_node[SMEM_STACK * TRACE_THREADS];
-    __shared__ float sh_dist[SMEM_STACK * TRACE_THREADS];
-    const uint32_t n = *n_ptr;
-    const int lane = threadIdx.x & 31;
-    Stack st;
-    st.s_node = sh_node + threadIdx.x;
-    st.s_dist = sh_dist + threadIdx.x;
-    for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(work_ctr, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        const uint32_t pos = base + lane;
-        if (pos < n) {
-            const RaySetup r = make_ray(ldg4(qo + pos), ldg4(qd + pos), s.lpad_scale);
-            float sum = 0.0f;
-            st.sp = 0;
-            int cur = 0;
-            for (;;) {
-                while (cur >= 0) {
-                    const float4* nd = s.lnodes + (size_t)cur * 8;
-                    const float4 nxp = ldg4(nd + r.sx), fxp = ldg4(nd + (r.sx ^ 1));
-                    const float4 nyp = ldg4(nd + r.sy), fyp = ldg4(nd + (r.sy ^ 1));
-                    const float4 nzp = ldg4(nd + r.sz), fzp = ldg4(nd + (r.sz ^ 1));
-                    const int4 ch = __ldg(reinterpret_cast<const int4*>(nd + 6));
-                    int next = WIDE_EMPTY;
-#define ORT_BOX(k, C)                                                                             \
-    {                                                                                             \
-        float tn = fmaxf(fmaxf(fmaf(nxp.k, r.ix, r.nx), fmaf(nyp.k, r.iy, r.ny)),                 \
-                         fmaxf(fmaf(nzp.k, r.iz, r.nz), 0.0f));                                   \
-        float tf = fminf(fminf(fmaf(fxp.k, r.ix, r.fx), fmaf(fyp.k, r.iy, r.fy)),                 \
-                         fmaf(fzp.k, r.iz, r.fz));                                                \
-        if (tn <= tf && C != WIDE_EMPTY) {                                                        \
-            if (next != WIDE_EMPTY) st.push(next, 0.0f);                                          \
-            next = C;                                                                             \
-        }                                                                                         \
-    }
-                    ORT_BOX(x, ch.x) ORT_BOX(y, ch.y) ORT_BOX(z, ch.z) ORT_BOX(w, ch.w)
-#undef ORT_BOX
-                    if (next == WIDE_EMPTY && st.sp > 0) { float dd; st.pop(next, dd); }
-                    cur = next;
-                }
-                if (cur == WIDE_EMPTY) break;
-                {
-                    const uint32_t code = (uint32_t)~cur;
-                    const uint32_t first = code >> 3, cnt = code & 7u;
-                    for (uint32_t i = 0; i < cnt; i++) {
-                        const float4* tp = s.ltris + (size_t)(first + i) * 3;
-                        const float4 a = ldg4(tp), b = ldg4(tp + 1), c = ldg4(tp + 2);
-                        float id, bx, by, bz, t, a00, a10, u, v;
-                        tri_det_t(r, a, b, c, id, bx, by, bz, t, a00, a10);
-                        // reference: intersect returns t = -1 when (u,v) is outside, then `!(t >= 0)` skips
-                        if (t >= 0.0f && tri_uv(r, a, b, c, id, bx, by, bz, a00, a10, u, v)) {
-                            const float4 L = ldg4(s.llight + (first + i));
-                            const float weight = (t * t) / fabsf(L.x * r.dx + L.y * r.dy + L.z * r.dz);
-                            sum += L.w * weight;
-                        }
-                    }
-                }
-                cur = WIDE_EMPTY;
-                if (st.sp > 0) { float dd; st.pop(cur, dd); }
-                if (cur == WIDE_EMPTY) break;
-            }
-            lsum[pos] = sum;
-        }
-    }
-}
+} // namespace ort
+#include "traverse.cuh"
+namespace ort {
 
 // ------------------------------------------------------------------------------------------------
 // k_raygen: primary rays (raytracer.odin:580-586).  slot = s_local * npix + (py*w + px).

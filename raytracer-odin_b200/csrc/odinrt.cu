@@ -1,13 +1,14 @@
 // odinrt.cu — context, scene upload, wavefront scheduling and the C ABI of libodinrt_b200.so
 // (include/odinrt_b200.h).  Replaces render_scene / render_task (raytracer.odin:528-665): the
 // atomic tile counter and OS threads become waves of (pixel x sample) paths advanced one bounce
-// at a time by k_trace / k_light / k_shade, with queue sizes living on the device so a whole wave
+// at a time by k_trace (closest hit + fused light-pdf sum) / k_shade, with queue sizes living on the device so a whole wave
 // is enqueued without any host synchronisation.
 #include <cuda_runtime.h>
 
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -56,7 +57,10 @@ struct ort_ctx {
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
 
-    int trace_grid = 0, light_grid = 0, shade_grid = 0;
+    int trace_grid = 0, light_grid = 0, fused_grid = 0, shade_grid = 0;
+    int fuse = 0; // env ORT_FUSE=1: trace closest hit + light sum in one fused pass
+    int refill = ORT_REFILL_THRESHOLD; // dynamic-fetch threshold (env ORT_REFILL, for tuning)
+    int inner_min = ORT_INNER_MIN;     // inner-loop early-exit threshold (env ORT_INNER_MIN, for tuning)
     bool profiling = false;
     double ms_trace = 0, ms_light = 0, ms_shade = 0, ms_other = 0, ms_render = 0;
     uint64_t launches = 0;
@@ -205,6 +209,18 @@ int ensure_pinned(ort_ctx* ctx, size_t bytes) {
     return 0;
 }
 
+// mode 0: closest hit, 1: light-pdf sum, 2: both fused in one pass
+void launch_trace(ort_ctx* ctx, const float4* qo, const float4* qd, const uint32_t* n_ptr, uint32_t* work_ctr, int mode) {
+    TraceArgs a;
+    a.qo = qo; a.qd = qd; a.n_ptr = n_ptr; a.work_ctr = work_ctr;
+    a.hits = ctx->hits; a.lsum = ctx->lsum;
+    a.refill_threshold = ctx->refill; a.inner_min = ctx->inner_min;
+    if (mode == 0) k_trace<true, false><<<ctx->trace_grid, TRACE_THREADS, 0, ctx->stream>>>(ctx->sd, a);
+    else if (mode == 1) k_trace<false, true><<<ctx->light_grid, TRACE_THREADS, 0, ctx->stream>>>(ctx->sd, a);
+    else k_trace<true, true><<<ctx->fused_grid, TRACE_THREADS, 0, ctx->stream>>>(ctx->sd, a);
+    ctx->launches++;
+}
+
 struct Prof {
     ort_ctx* c;
     double* acc;
@@ -250,15 +266,14 @@ int launch_wave(ort_ctx* ctx, const RenderParams& p, float* d_accum, float* d_fi
     }
     for (int k = 0; k < D; k++) {
         const int in = k & 1, out = in ^ 1;
+        const bool need_light = k > 0 && lights; // bounce 0 has no pending pdf to complete
         {
             Prof pr(ctx, &ctx->ms_trace);
-            k_trace<<<ctx->trace_grid, TRACE_THREADS, 0, st>>>(ctx->sd, ctx->qo[in], ctx->qd[in], counts + k, wtrace + k, ctx->hits);
-            ctx->launches++;
+            launch_trace(ctx, ctx->qo[in], ctx->qd[in], counts + k, wtrace + k, (need_light && ctx->fuse) ? 2 : 0);
         }
-        if (k > 0 && lights) {
+        if (need_light && !ctx->fuse) {
             Prof pr(ctx, &ctx->ms_light);
-            k_light<<<ctx->light_grid, TRACE_THREADS, 0, st>>>(ctx->sd, ctx->qo[in], ctx->qd[in], counts + k, wlight + k, ctx->lsum);
-            ctx->launches++;
+            launch_trace(ctx, ctx->qo[in], ctx->qd[in], counts + k, wlight + k, 1);
         }
         {
             Prof pr(ctx, &ctx->ms_shade);
@@ -344,6 +359,9 @@ int ort_create(ort_ctx** out, const ort_device_cfg* cfg) {
     c->sm_count = prop.multiProcessorCount;
     c->seed = cfg ? cfg->seed : 0;
     c->capacity_cfg = cfg ? cfg->max_paths_in_flight : 0;
+    if (const char* e2 = std::getenv("ORT_REFILL")) c->refill = std::atoi(e2);
+    if (const char* e2 = std::getenv("ORT_INNER_MIN")) c->inner_min = std::atoi(e2);
+    if (const char* e2 = std::getenv("ORT_FUSE")) c->fuse = std::atoi(e2);
     ctx = c;
     auto bail = [&](const char* what, cudaError_t err) {
         g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
@@ -358,10 +376,12 @@ int ort_create(ort_ctx** out, const ort_device_cfg* cfg) {
     cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long));
     // persistent grids: as many CTAs as stay resident, a multiple of the SM count
     int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace, TRACE_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<true, false>, TRACE_THREADS, 0);
     c->trace_grid = c->sm_count * std::max(occ, 1);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_light, TRACE_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<false, true>, TRACE_THREADS, 0);
     c->light_grid = c->sm_count * std::max(occ, 1);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<true, true>, TRACE_THREADS, 0);
+    c->fused_grid = c->sm_count * std::max(occ, 1);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shade, 256, 0);
     c->shade_grid = c->sm_count * std::max(occ, 1);
     *out = c;
@@ -387,7 +407,7 @@ int ort_set_stream(ort_ctx* ctx, void* cuda_stream) {
     if (!ctx) return 1;
     Bind b(ctx->device);
     CK(cudaStreamSynchronize(ctx->stream));
-    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    ctx->stream = cuda_stream == ORT_OWN_STREAM ? ctx->own_stream : (cudaStream_t)cuda_stream;
     return 0;
 }
 
@@ -422,20 +442,36 @@ int ort_upload_scene(ort_ctx* ctx, const ort_scene* sc) {
     ctx->n_tris = sc->n_triangles;
     ctx->n_ltris = sc->n_light_triangles;
     SceneDev sd{};
-    if (upload<float4>(ctx, ctx->wide.nodes.data(), ctx->wide.nodes.size() * 8, &sd.nodes)) return 1;
-    if (upload<float4>(ctx, ctx->lwide.nodes.data(), ctx->lwide.nodes.size() * 8, &sd.lnodes)) return 1;
     {
-        std::vector<TriIsect> rec((size_t)sc->n_triangles);
-        make_isect_records(sc->triangles, sc->n_triangles, rec.data());
-        if (upload<float4>(ctx, rec.data(), rec.size() * 3, &sd.tris)) return 1;
-        CK(cudaStreamSynchronize(ctx->stream));
-    }
-    {
-        std::vector<TriIsect> rec((size_t)sc->n_light_triangles);
+        // one node array (scene BVH, root 0, then the light BVH) and one traversal-triangle array
+        // (scene triangles, then the light triangles): a ray walks both trees with the same code
+        const size_t ns = ctx->wide.nodes.size(), nl = ctx->lwide.nodes.size();
+        std::vector<WideNode> nodes(ns + nl);
+        std::memcpy(nodes.data(), ctx->wide.nodes.data(), ns * sizeof(WideNode));
+        for (size_t i = 0; i < nl; i++) {
+            WideNode w = ctx->lwide.nodes[i];
+            for (int k = 0; k < 4; k++) {
+                if (w.child[k] == WIDE_EMPTY) continue;
+                if (w.child[k] >= 0) w.child[k] += (int32_t)ns;
+                else {
+                    const uint32_t code = (uint32_t)~w.child[k];
+                    w.child[k] = ~(int32_t)((((code >> 3) + (uint32_t)sc->n_triangles) << 3) | (code & 7u));
+                }
+            }
+            nodes[ns + i] = w;
+        }
+        if ((uint64_t)sc->n_triangles + (uint64_t)sc->n_light_triangles >= (1u << 28))
+            return fail(ctx, "ort_upload_scene: more than 2^28 traversal triangles");
+        if (upload<float4>(ctx, nodes.data(), nodes.size() * 8, &sd.nodes)) return 1;
+        sd.light_root = (int32_t)ns;
+        sd.light_tri_base = (uint32_t)sc->n_triangles;
+        std::vector<TriIsect> rec((size_t)(sc->n_triangles + sc->n_light_triangles));
         std::vector<TriLight> lrec((size_t)sc->n_light_triangles);
-        make_isect_records(sc->light_triangles, sc->n_light_triangles, rec.data());
+        make_isect_records(sc->triangles, sc->n_triangles, rec.data());
+        make_isect_records(sc->light_triangles, sc->n_light_triangles, rec.data() + sc->n_triangles);
         make_light_records(sc->light_triangles, sc->n_light_triangles, lrec.data());
-        if (upload<float4>(ctx, rec.data(), rec.size() * 3, &sd.ltris)) return 1;
+        if (upload<float4>(ctx, rec.data(), rec.size() * 3, &sd.tris)) return 1;
+        sd.ltris = sd.tris + (size_t)sc->n_triangles * 3;
         if (upload<float4>(ctx, lrec.data(), lrec.size(), &sd.llight)) return 1;
         CK(cudaStreamSynchronize(ctx->stream));
     }
@@ -512,7 +548,6 @@ int ort_upload_scene(ort_ctx* ctx, const ort_scene* sc) {
     }
     sd.n_lights = (int32_t)sc->n_light_triangles;
     std::memcpy(sd.pad_scale, ctx->wide.max_abs, 12);
-    std::memcpy(sd.lpad_scale, ctx->lwide.max_abs, 12);
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->sd = sd;
     ctx->has_scene = true;
@@ -604,9 +639,9 @@ int ort_trace_rays(ort_ctx* ctx, const ort_ray* rays, int64_t n, ort_hit* out) {
         CK(cudaMemcpyAsync(d_in, rays + off, (size_t)m * 24, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemsetAsync(ctx->counters, 0, sizeof(uint32_t) * 8, ctx->stream));
         k_pack_rays<<<ctx->shade_grid, 256, 0, ctx->stream>>>(d_in, m, ctx->qo[0], ctx->qd[0], ctx->counters);
-        k_trace<<<ctx->trace_grid, TRACE_THREADS, 0, ctx->stream>>>(ctx->sd, ctx->qo[0], ctx->qd[0], ctx->counters, ctx->counters + 1, ctx->hits);
+        launch_trace(ctx, ctx->qo[0], ctx->qd[0], ctx->counters, ctx->counters + 1, 0);
         k_unpack_hits<<<ctx->shade_grid, 256, 0, ctx->stream>>>(ctx->sd, ctx->hits, ctx->qd[0], m, d_out);
-        ctx->launches += 3;
+        ctx->launches += 2;
         CK(cudaMemcpyAsync(out + off, d_out, (size_t)m * 24, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
@@ -629,9 +664,9 @@ int ort_light_pdf(ort_ctx* ctx, const ort_ray* rays, int64_t n, float* out) {
         CK(cudaMemcpyAsync(ctx->scratch, rays + off, (size_t)m * 24, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemsetAsync(ctx->counters, 0, sizeof(uint32_t) * 8, ctx->stream));
         k_pack_rays<<<ctx->shade_grid, 256, 0, ctx->stream>>>(ctx->scratch, m, ctx->qo[0], ctx->qd[0], ctx->counters);
-        k_light<<<ctx->light_grid, TRACE_THREADS, 0, ctx->stream>>>(ctx->sd, ctx->qo[0], ctx->qd[0], ctx->counters, ctx->counters + 1, ctx->lsum);
+        launch_trace(ctx, ctx->qo[0], ctx->qd[0], ctx->counters, ctx->counters + 1, 1);
         k_scale<<<ctx->shade_grid, 256, 0, ctx->stream>>>(ctx->lsum, m, (float)ctx->sd.n_lights);
-        ctx->launches += 3;
+        ctx->launches += 2;
         CK(cudaMemcpyAsync(out + off, ctx->lsum, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
@@ -654,9 +689,9 @@ int ort_primary_hits(ort_ctx* ctx, uint32_t w, uint32_t h, uint64_t sample, ort_
     p.n_batch_samples = 1;
     CK(cudaMemsetAsync(ctx->counters, 0, sizeof(uint32_t) * 8, ctx->stream));
     k_raygen<<<ctx->shade_grid, 256, 0, ctx->stream>>>(p, ctx->qo[0], ctx->qd[0], ctx->counters);
-    k_trace<<<ctx->trace_grid, TRACE_THREADS, 0, ctx->stream>>>(ctx->sd, ctx->qo[0], ctx->qd[0], ctx->counters, ctx->counters + 1, ctx->hits);
+    launch_trace(ctx, ctx->qo[0], ctx->qd[0], ctx->counters, ctx->counters + 1, 0);
     k_unpack_hits<<<ctx->shade_grid, 256, 0, ctx->stream>>>(ctx->sd, ctx->hits, ctx->qd[0], (uint32_t)npix, ctx->scratch);
-    ctx->launches += 3;
+    ctx->launches += 2;
     CK(cudaMemcpyAsync(out, ctx->scratch, npix * 24, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     if (rays_out) {

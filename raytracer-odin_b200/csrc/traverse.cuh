@@ -1,0 +1,223 @@
+// traverse.cuh — k_trace: closest hit (cast_ray, raytracer.odin:416-430) and, fused behind it for
+// continuation rays, the light-BVH all-hit pdf sum of the same ray
+// (surface_sampling_pdf_bvh_sum, shading.odin:62-94).
+//
+// Design notes (every choice below was measured on B200, see profiles/):
+//   * Software BVH traversal here is ISSUE bound, not bandwidth bound (DRAM < 4 %, L2 ~ 12 % of
+//     peak, issue slots ~ 70 % busy), and its enemy is SIMD divergence: the first version (warp
+//     fetches 32 rays, runs until the slowest is done) executed with 6 of 32 lanes active.
+//   * Persistent threads with PER-LANE dynamic fetch: when fewer than `refill_threshold` lanes of
+//     a warp still hold a ray, the warp leaves the traversal loop (in-flight rays keep their state
+//     in registers and on the stack), idle lanes claim new rays from the compacted queue with ONE
+//     atomic per warp (ballot + prefix popcount), and everybody resumes.
+//   * while-while traversal with an early exit from the inner-node loop: lanes that found a leaf
+//     wait at the loop's end; once fewer than `inner_min` lanes are still descending, the loop is
+//     left so the waiting lanes test their triangles.  (A fully warp-synchronous "vote one step
+//     per iteration" variant was tried and was 20 % slower: profiles/r1_traversal_variants.md.)
+//   * The light BVH is appended to the scene's node / triangle arrays.  When a continuation ray's
+//     closest-hit stack runs dry the lane switches to phase 1 and walks the light tree with the
+//     same inner loop (no distance culling, no ordering needed) for the all-hit sum.
+//   * 4-wide nodes of one 128-byte line, near / far planes picked by per-ray byte offsets, 16-byte
+//     loads only; stack: first SMEM_STACK entries in shared memory ([entry][thread], conflict
+//     free), deeper entries in thread-local memory (exact worst case checked on the host).
+//
+// Numerics: box tests are conservative supersets of the reference's (see make_ray); the triangle
+// solve is the reference's arithmetic bit for bit (tri_det_t / tri_uv); triangles of a leaf are
+// tested in reference order with strict `<`, so the first one wins exact ties inside a leaf.
+#pragma once
+#include "device_math.cuh"
+#include "wide_bvh.h"
+
+namespace ort {
+
+#ifndef ORT_REFILL_THRESHOLD
+#define ORT_REFILL_THRESHOLD 22
+#endif
+#ifndef ORT_INNER_MIN
+#define ORT_INNER_MIN 12
+#endif
+
+#define ORT_PUSH(NODE, DIST)                                                                          \
+    {                                                                                                 \
+        if (sp < SMEM_STACK) { sh_node[sp][threadIdx.x] = (NODE); sh_dist[sp][threadIdx.x] = (DIST); } \
+        else { l_node[sp - SMEM_STACK] = (NODE); l_dist[sp - SMEM_STACK] = (DIST); }                  \
+        sp++;                                                                                         \
+    }
+#define ORT_POP(NODE, DIST)                                                                           \
+    {                                                                                                 \
+        sp--;                                                                                         \
+        if (sp < SMEM_STACK) { NODE = sh_node[sp][threadIdx.x]; DIST = sh_dist[sp][threadIdx.x]; }    \
+        else { NODE = l_node[sp - SMEM_STACK]; DIST = l_dist[sp - SMEM_STACK]; }                      \
+    }
+#define ORT_CSWAP(da, ca, db, cb)               \
+    {                                           \
+        const bool sw_ = db < da;               \
+        const float td_ = sw_ ? db : da;        \
+        const int tc_ = sw_ ? cb : ca;          \
+        db = sw_ ? da : db; cb = sw_ ? ca : cb; \
+        da = td_; ca = tc_;                     \
+    }
+
+struct TraceArgs {
+    const float4* qo;       // ray origins (xyz) + path slot (w), compacted queue order
+    const float4* qd;       // ray directions
+    const uint32_t* n_ptr;  // queue size (device resident)
+    uint32_t* work_ctr;     // persistent-thread work counter
+    float4* hits;           // out: (t, u, v, tri)
+    float* lsum;            // out: light pdf sum (only when do_light)
+    int refill_threshold;   // dynamic fetch when fewer lanes than this hold a ray
+    int inner_min;          // leave the inner-node loop when fewer lanes than this remain in it
+};
+
+// CLOSEST / LIGHT select the phases compiled in: <true,false> closest hit only (what render uses for
+// every bounce), <false,true> light sum only (render, bounces > 0), <true,true> both fused in one
+// pass (kept for comparison: 77 registers and phase-divergent leaf code make it 15 % slower than
+// the two specialised launches, profiles/r1_traversal_variants.md).
+template <bool CLOSEST, bool LIGHT>
+__global__ void __launch_bounds__(TRACE_THREADS)
+k_trace(const SceneDev s, const TraceArgs a) {
+    __shared__ int sh_node[SMEM_STACK][TRACE_THREADS];
+    __shared__ float sh_dist[SMEM_STACK][TRACE_THREADS];
+    int l_node[LOCAL_STACK];
+    float l_dist[LOCAL_STACK];
+
+    const uint32_t n = *a.n_ptr;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const float best_pad = 1.0f + 7.62939453125e-06f; // 1 + 2^-17: distance culling margin
+    const float inf = __int_as_float(0x7f800000);
+
+    RaySetup r;
+    float best = inf, hu = 0.0f, hv = 0.0f, lsumv = 0.0f;
+    float cull = inf;       // pop / box limit: best * best_pad in phase 0, +inf in phase 1
+    int htri = -1, sp = 0, cur = WIDE_EMPTY;
+    int phase = 0;          // 0: closest hit on the scene BVH, 1: all-hit sum on the light BVH
+    uint32_t pos = 0;
+    bool exhausted = false; // warp-uniform: the queue has no unclaimed rays left
+
+    for (;;) {
+        // ---- refill idle lanes (dynamic fetch)
+        const bool idle = cur == WIDE_EMPTY;
+        const unsigned idle_mask = __ballot_sync(0xffffffffu, idle);
+        if (idle_mask != 0u && !exhausted) {
+            const int cnt = __popc(idle_mask);
+            const int leader = __ffs(idle_mask) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(a.work_ctr, (uint32_t)cnt);
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (idle) {
+                const uint32_t idx = base + __popc(idle_mask & lt_mask);
+                if (idx < n) {
+                    r = make_ray(ldg4(a.qo + idx), ldg4(a.qd + idx), s.pad_scale);
+                    best = inf; hu = 0.0f; hv = 0.0f; htri = -1; lsumv = 0.0f; // max_dist = +inf (raytracer.odin:435)
+                    cull = inf; sp = 0; pos = idx;
+                    if (!CLOSEST) { phase = 1; cur = s.light_root; }
+                    else { phase = 0; cur = 0; }
+                }
+            }
+            exhausted = base + (uint32_t)cnt >= n;
+        }
+        if (__ballot_sync(0xffffffffu, cur != WIDE_EMPTY) == 0u) break;
+
+        // ---- traverse
+        if (cur != WIDE_EMPTY) {
+            for (;;) {
+                while (cur >= 0) {
+                    const float4* nd = s.nodes + (size_t)cur * 8;
+                    const float4 nxp = ldg4(nd + r.sx), fxp = ldg4(nd + (r.sx ^ 1));
+                    const float4 nyp = ldg4(nd + r.sy), fyp = ldg4(nd + (r.sy ^ 1));
+                    const float4 nzp = ldg4(nd + r.sz), fzp = ldg4(nd + (r.sz ^ 1));
+                    const int4 ch = __ldg(reinterpret_cast<const int4*>(nd + 6));
+                    float d0, d1, d2, d3;
+                    int c0 = ch.x, c1 = ch.y, c2 = ch.z, c3 = ch.w;
+#define ORT_BOX(k, D, C)                                                                          \
+    {                                                                                             \
+        const float tn = fmaxf(fmaxf(fmaf(nxp.k, r.ix, r.nx), fmaf(nyp.k, r.iy, r.ny)),           \
+                               fmaxf(fmaf(nzp.k, r.iz, r.nz), 0.0f));                             \
+        const float tf = fminf(fminf(fmaf(fxp.k, r.ix, r.fx), fmaf(fyp.k, r.iy, r.fy)),           \
+                               fminf(fmaf(fzp.k, r.iz, r.fz), cull));                             \
+        D = (tn <= tf && C != WIDE_EMPTY) ? tn : inf;                                             \
+    }
+                    ORT_BOX(x, d0, c0) ORT_BOX(y, d1, c1) ORT_BOX(z, d2, c2) ORT_BOX(w, d3, c3)
+#undef ORT_BOX
+                    const int nh = (d0 < inf) + (d1 < inf) + (d2 < inf) + (d3 < inf);
+                    ORT_CSWAP(d0, c0, d1, c1) ORT_CSWAP(d2, c2, d3, c3) ORT_CSWAP(d0, c0, d2, c2)
+                    ORT_CSWAP(d1, c1, d3, c3) ORT_CSWAP(d1, c1, d2, c2)
+                    if (nh == 0) {
+                        cur = WIDE_EMPTY; // pop, skipping entries the current best already culls
+                        while (sp > 0) {
+                            int nd2; float dd;
+                            ORT_POP(nd2, dd)
+                            if (dd <= cull) { cur = nd2; break; }
+                        }
+                    } else {
+                        if (nh > 3) ORT_PUSH(c3, d3)
+                        if (nh > 2) ORT_PUSH(c2, d2)
+                        if (nh > 1) ORT_PUSH(c1, d1)
+                        cur = c0;
+                    }
+                    // lanes that already hold a leaf wait at the end of this loop: once too few lanes
+                    // are still descending, stop and let the waiting lanes test their triangles
+                    if (__popc(__activemask()) < a.inner_min) break;
+                }
+                if (cur < 0 && cur != WIDE_EMPTY) {
+                    const uint32_t code = (uint32_t)~cur;
+                    const uint32_t first = code >> 3, cnt = code & 7u;
+                    if (CLOSEST && (!LIGHT || phase == 0)) {
+                        // cast_ray_through_trigs (raytracer.odin:351-369): reference order, first wins ties
+                        for (uint32_t i = 0; i < cnt; i++) {
+                            const float4* tp = s.tris + (size_t)(first + i) * 3;
+                            const float4 ta = ldg4(tp), tb = ldg4(tp + 1), tc = ldg4(tp + 2);
+                            float id, bx, by, bz, t, a00, a10;
+                            tri_det_t(r, ta, tb, tc, id, bx, by, bz, t, a00, a10);
+                            if (t > 0.0f && t < best) { // raytracer.odin:360
+                                float u, v;
+                                if (tri_uv(r, ta, tb, tc, id, bx, by, bz, a00, a10, u, v)) {
+                                    best = t; hu = u; hv = v; htri = (int)(first + i);
+                                    cull = best * best_pad;
+                                }
+                            }
+                        }
+                    } else {
+                        // surface_sampling_pdf_trigs_sum (shading.odin:52-60): the reference's intersect
+                        // returns t = -1 when (u,v) is outside, then `!(t >= 0)` skips
+                        for (uint32_t i = 0; i < cnt; i++) {
+                            const float4* tp = s.tris + (size_t)(first + i) * 3;
+                            const float4 ta = ldg4(tp), tb = ldg4(tp + 1), tc = ldg4(tp + 2);
+                            float id, bx, by, bz, t, a00, a10, u, v;
+                            tri_det_t(r, ta, tb, tc, id, bx, by, bz, t, a00, a10);
+                            if (t >= 0.0f && tri_uv(r, ta, tb, tc, id, bx, by, bz, a00, a10, u, v)) {
+                                const float4 L = ldg4(s.llight + (first + i - s.light_tri_base));
+                                const float weight = (t * t) / fabsf(L.x * r.dx + L.y * r.dy + L.z * r.dz);
+                                lsumv += L.w * weight;
+                            }
+                        }
+                    }
+                    cur = WIDE_EMPTY;
+                    while (sp > 0) {
+                        int nd2; float dd;
+                        ORT_POP(nd2, dd)
+                        if (dd <= cull) { cur = nd2; break; }
+                    }
+                }
+                if (cur == WIDE_EMPTY) {
+                    if (CLOSEST && LIGHT && phase == 0) {
+                        // closest hit known; now the light-BVH all-hit sum of the same ray
+                        phase = 1; cull = inf; cur = s.light_root;
+                    } else {
+                        if (CLOSEST) a.hits[pos] = make_float4(htri >= 0 ? best : 0.0f, hu, hv, __int_as_float(htri));
+                        if (LIGHT) a.lsum[pos] = lsumv;
+                        break; // ray finished
+                    }
+                }
+                if (!exhausted && __popc(__activemask()) < a.refill_threshold) break; // go refill
+            }
+        }
+    }
+}
+
+#undef ORT_PUSH
+#undef ORT_POP
+#undef ORT_CSWAP
+
+} // namespace ort
