@@ -122,7 +122,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("ORT_LIB") or LIB_PATH  # ORT_LIB: a tuning variant built by `make variant`
     if not os.path.exists(p):
         raise RuntimeError(
             f"{p} is missing: the CUDA library is the product and there is no CPU fallback. "

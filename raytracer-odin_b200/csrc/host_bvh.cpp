@@ -264,6 +264,65 @@ bool build_wide_bvh(const ort_bvh_node* bvh, int64_t n_nodes, int64_t n_tris, Wi
     return true;
 }
 
+void quantize_wide_nodes(const WideNode* in, size_t n, QuantNode* out) {
+    for (size_t i = 0; i < n; i++) {
+        const WideNode& w = in[i];
+        QuantNode q;
+        std::memset(&q, 0, sizeof q);
+        for (int k = 0; k < 4; k++) q.child[k] = w.child[k];
+        for (int ax = 0; ax < 3; ax++) {
+            double lo = std::numeric_limits<double>::infinity(), hi = -lo;
+            for (int k = 0; k < 4; k++) {
+                if (w.child[k] == WIDE_EMPTY) continue;
+                lo = std::min(lo, (double)w.bounds[ax][0][k]);
+                hi = std::max(hi, (double)w.bounds[ax][1][k]);
+            }
+            if (!(lo <= hi) || !std::isfinite(lo) || !std::isfinite(hi)) { lo = 0; hi = 0; } // no children / non-finite
+            // smallest power-of-two step with 250 steps >= extent (headroom for the slack and for
+            // moving the origin one step below the lowest plane, so that plane keeps its slack too)
+            int e = 1;
+            const double extent = hi - lo;
+            if (extent > 0) {
+                int ex;
+                std::frexp(extent / 250.0, &ex); // extent/250 = m * 2^ex, m in [0.5, 1)  ->  2^ex >= extent/250
+                e = ex + 127;
+            }
+            e = std::max(1, std::min(e, 254 - 15)); // the kernel multiplies the step by 2^15
+            float origin = 0.0f;
+            for (;;) {
+                const double step = std::ldexp(1.0, e - 127);
+                const double slack = step / 128.0; // covers the kernel's decode rounding (2^-9 step) generously
+                origin = (float)(lo - step);
+                if ((double)origin > lo - step) origin = std::nextafterf(origin, -std::numeric_limits<float>::infinity());
+                if (!std::isfinite(origin)) origin = (float)lo;
+                bool ok = true;
+                uint32_t wlo = 0, whi = 0;
+                for (int k = 0; k < 4; k++) {
+                    uint32_t ql = 255, qh = 0; // unused slot: inverted, never hit (and flagged by child)
+                    if (w.child[k] != WIDE_EMPTY) {
+                        double a = std::floor(((double)w.bounds[ax][0][k] - slack - origin) / step);
+                        double b = std::ceil(((double)w.bounds[ax][1][k] + slack - origin) / step);
+                        if (!(a == a)) a = 0;   // NaN inputs: keep the node harmless
+                        if (!(b == b)) b = 255;
+                        if (a < 0) a = 0;
+                        if (b > 255) { ok = false; break; }
+                        ql = (uint32_t)a; qh = (uint32_t)b;
+                    }
+                    wlo |= ql << (8 * k);
+                    whi |= qh << (8 * k);
+                }
+                if (ok) { q.planes[ax][0] = wlo; q.planes[ax][1] = whi; break; }
+                if (++e > 254 - 15) { // cannot happen for finite input; degrade to "everything"
+                    q.planes[ax][0] = 0; q.planes[ax][1] = 0xffffffffu; e = 254 - 15; break;
+                }
+            }
+            q.origin[ax] = origin;
+            q.exps |= (uint32_t)e << (8 * ax);
+        }
+        out[i] = q;
+    }
+}
+
 void make_isect_records(const ort_triangle* tris, int64_t n, TriIsect* out) {
     for (int64_t i = 0; i < n; i++) {
         const ort_triangle& t = tris[i];

@@ -18,9 +18,15 @@ constexpr float RAY_EPS = 1e-3f; // raytracer.odin:418, shading.odin:66
 constexpr float PI_F = 3.14159265358979323846264338327950288f;
 constexpr float TAU_F = 6.28318530717958647692528676655900576f;
 
+#ifndef ORT_SMEM_STACK
+#define ORT_SMEM_STACK 16
+#endif
+#ifndef ORT_TRACE_MIN_CTAS
+#define ORT_TRACE_MIN_CTAS 1
+#endif
 constexpr int TRACE_THREADS = 128;
-constexpr int SMEM_STACK = 16;   // stack entries per thread kept in shared memory
-constexpr int LOCAL_STACK = 112; // overflow entries per thread in local memory
+constexpr int SMEM_STACK = ORT_SMEM_STACK;        // stack entries per thread kept in shared memory
+constexpr int LOCAL_STACK = 128 - ORT_SMEM_STACK; // overflow entries per thread in local memory
 constexpr int MAX_STACK = SMEM_STACK + LOCAL_STACK;
 
 struct DevMaterial {
@@ -86,7 +92,12 @@ __device__ __forceinline__ RaySetup make_ray(float4 o4, float4 d4, const float* 
     r.ox = addr(o4.x, mulr(d4.x, RAY_EPS));
     r.oy = addr(o4.y, mulr(d4.y, RAY_EPS));
     r.oz = addr(o4.z, mulr(d4.z, RAY_EPS));
+#ifdef ORT_FAST_RCP
+    // the slab distances are padded by 16 ulp anyway: a 1-ulp approximate reciprocal is enough
+    r.ix = __frcp_rn(r.dx); r.iy = __frcp_rn(r.dy); r.iz = __frcp_rn(r.dz);
+#else
     r.ix = 1.0f / r.dx; r.iy = 1.0f / r.dy; r.iz = 1.0f / r.dz;
+#endif
     const float ulp16 = 16.0f * 5.9604645e-08f;
     float px = ulp16 * (fabsf(r.ox) + pad_scale[0]) * fabsf(r.ix);
     float py = ulp16 * (fabsf(r.oy) + pad_scale[1]) * fabsf(r.iy);
@@ -285,7 +296,10 @@ __device__ f3 brdf_cos(f3 color, f3 N, float metallic, float roughness, f3 in_d,
 // sum of the ray just traced is the missing third of pdf (shading.odin:153-162), then
 // `norm_l1(value)/pdf > 1e-5` (raytracer.odin:495) decides whether this hit counts at all.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+#ifndef ORT_SHADE_MIN_CTAS
+#define ORT_SHADE_MIN_CTAS 3
+#endif
+__global__ void __launch_bounds__(256, ORT_SHADE_MIN_CTAS)
 k_shade(const SceneDev s, const RenderParams p, const int bounce, const float4* __restrict__ qo_in,
         const float4* __restrict__ qd_in, const float4* __restrict__ hits, const float* __restrict__ lsum,
         const uint32_t* __restrict__ n_in_ptr, float4* __restrict__ qo_out, float4* __restrict__ qd_out,

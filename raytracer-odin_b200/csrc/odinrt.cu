@@ -57,7 +57,9 @@ struct ort_ctx {
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
 
-    int trace_grid = 0, light_grid = 0, fused_grid = 0, shade_grid = 0;
+    int trace_grid[2][3] = {{0, 0, 0}, {0, 0, 0}}; // [node encoding][mode] persistent grid sizes
+    int shade_grid = 0;
+    bool quant = false; // scene uses QuantNode
     int fuse = 0; // env ORT_FUSE=1: trace closest hit + light sum in one fused pass
     int refill = ORT_REFILL_THRESHOLD; // dynamic-fetch threshold (env ORT_REFILL, for tuning)
     int inner_min = ORT_INNER_MIN;     // inner-loop early-exit threshold (env ORT_INNER_MIN, for tuning)
@@ -215,9 +217,16 @@ void launch_trace(ort_ctx* ctx, const float4* qo, const float4* qd, const uint32
     a.qo = qo; a.qd = qd; a.n_ptr = n_ptr; a.work_ctr = work_ctr;
     a.hits = ctx->hits; a.lsum = ctx->lsum;
     a.refill_threshold = ctx->refill; a.inner_min = ctx->inner_min;
-    if (mode == 0) k_trace<true, false><<<ctx->trace_grid, TRACE_THREADS, 0, ctx->stream>>>(ctx->sd, a);
-    else if (mode == 1) k_trace<false, true><<<ctx->light_grid, TRACE_THREADS, 0, ctx->stream>>>(ctx->sd, a);
-    else k_trace<true, true><<<ctx->fused_grid, TRACE_THREADS, 0, ctx->stream>>>(ctx->sd, a);
+    const int g = ctx->trace_grid[ctx->quant ? 1 : 0][mode];
+    if (!ctx->quant) {
+        if (mode == 0) k_trace<true, false, false><<<g, TRACE_THREADS, 0, ctx->stream>>>(ctx->sd, a);
+        else if (mode == 1) k_trace<false, true, false><<<g, TRACE_THREADS, 0, ctx->stream>>>(ctx->sd, a);
+        else k_trace<true, true, false><<<g, TRACE_THREADS, 0, ctx->stream>>>(ctx->sd, a);
+    } else {
+        if (mode == 0) k_trace<true, false, true><<<g, TRACE_THREADS, 0, ctx->stream>>>(ctx->sd, a);
+        else if (mode == 1) k_trace<false, true, true><<<g, TRACE_THREADS, 0, ctx->stream>>>(ctx->sd, a);
+        else k_trace<true, true, true><<<g, TRACE_THREADS, 0, ctx->stream>>>(ctx->sd, a);
+    }
     ctx->launches++;
 }
 
@@ -376,12 +385,12 @@ int ort_create(ort_ctx** out, const ort_device_cfg* cfg) {
     cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long));
     // persistent grids: as many CTAs as stay resident, a multiple of the SM count
     int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<true, false>, TRACE_THREADS, 0);
-    c->trace_grid = c->sm_count * std::max(occ, 1);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<false, true>, TRACE_THREADS, 0);
-    c->light_grid = c->sm_count * std::max(occ, 1);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<true, true>, TRACE_THREADS, 0);
-    c->fused_grid = c->sm_count * std::max(occ, 1);
+#define ORT_OCC(Q, M, ...)                                                                     \
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<__VA_ARGS__>, TRACE_THREADS, 0); \
+    c->trace_grid[Q][M] = c->sm_count * std::max(occ, 1);
+    ORT_OCC(0, 0, true, false, false) ORT_OCC(0, 1, false, true, false) ORT_OCC(0, 2, true, true, false)
+    ORT_OCC(1, 0, true, false, true) ORT_OCC(1, 1, false, true, true) ORT_OCC(1, 2, true, true, true)
+#undef ORT_OCC
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shade, 256, 0);
     c->shade_grid = c->sm_count * std::max(occ, 1);
     *out = c;
@@ -462,7 +471,16 @@ int ort_upload_scene(ort_ctx* ctx, const ort_scene* sc) {
         }
         if ((uint64_t)sc->n_triangles + (uint64_t)sc->n_light_triangles >= (1u << 28))
             return fail(ctx, "ort_upload_scene: more than 2^28 traversal triangles");
-        if (upload<float4>(ctx, nodes.data(), nodes.size() * 8, &sd.nodes)) return 1;
+        // node encoding: f32 planes for small trees (issue bound), 8-bit planes for large ones
+        // (L1/TEX bound) — see traverse.cuh; ORT_QUANT=0/1 forces one (tuning / tests)
+        ctx->quant = nodes.size() * sizeof(WideNode) > ((size_t)48 << 20); // beyond ~L2/2 the smaller nodes win on capacity
+        if (const char* e2 = std::getenv("ORT_QUANT")) ctx->quant = std::atoi(e2) != 0;
+        if (ctx->quant) {
+            std::vector<QuantNode> qn(nodes.size());
+            quantize_wide_nodes(nodes.data(), nodes.size(), qn.data());
+            if (upload<float4>(ctx, qn.data(), qn.size() * 4, &sd.nodes)) return 1;
+            CK(cudaStreamSynchronize(ctx->stream));
+        } else if (upload<float4>(ctx, nodes.data(), nodes.size() * 8, &sd.nodes)) return 1;
         sd.light_root = (int32_t)ns;
         sd.light_tri_base = (uint32_t)sc->n_triangles;
         std::vector<TriIsect> rec((size_t)(sc->n_triangles + sc->n_light_triangles));

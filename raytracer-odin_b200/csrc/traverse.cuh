@@ -73,8 +73,12 @@ struct TraceArgs {
 // every bounce), <false,true> light sum only (render, bounces > 0), <true,true> both fused in one
 // pass (kept for comparison: 77 registers and phase-divergent leaf code make it 15 % slower than
 // the two specialised launches, profiles/r1_traversal_variants.md).
-template <bool CLOSEST, bool LIGHT>
-__global__ void __launch_bounds__(TRACE_THREADS)
+//
+// QUANT selects the node encoding: WideNode (f32 planes, 7 x LDG.128 per visit) or QuantNode (8-bit
+// planes, 4 x LDG.128 per visit, ~35 % more ALU per visit).  Small scenes are issue bound and run
+// faster on WideNode; large scenes are bound by the L1/TEX pipe and run faster on QuantNode.
+template <bool CLOSEST, bool LIGHT, bool QUANT>
+__global__ void __launch_bounds__(TRACE_THREADS, ORT_TRACE_MIN_CTAS)
 k_trace(const SceneDev s, const TraceArgs a) {
     __shared__ int sh_node[SMEM_STACK][TRACE_THREADS];
     __shared__ float sh_dist[SMEM_STACK][TRACE_THREADS];
@@ -91,6 +95,9 @@ k_trace(const SceneDev s, const TraceArgs a) {
     float best = inf, hu = 0.0f, hv = 0.0f, lsumv = 0.0f;
     float cull = inf;       // pop / box limit: best * best_pad in phase 0, +inf in phase 1
     int htri = -1, sp = 0, cur = WIDE_EMPTY;
+#ifdef ORT_SPECULATE
+    int parked = WIDE_EMPTY;
+#endif
     int phase = 0;          // 0: closest hit on the scene BVH, 1: all-hit sum on the light BVH
     uint32_t pos = 0;
     bool exhausted = false; // warp-uniform: the queue has no unclaimed rays left
@@ -123,13 +130,15 @@ k_trace(const SceneDev s, const TraceArgs a) {
         if (cur != WIDE_EMPTY) {
             for (;;) {
                 while (cur >= 0) {
-                    const float4* nd = s.nodes + (size_t)cur * 8;
-                    const float4 nxp = ldg4(nd + r.sx), fxp = ldg4(nd + (r.sx ^ 1));
-                    const float4 nyp = ldg4(nd + r.sy), fyp = ldg4(nd + (r.sy ^ 1));
-                    const float4 nzp = ldg4(nd + r.sz), fzp = ldg4(nd + (r.sz ^ 1));
-                    const int4 ch = __ldg(reinterpret_cast<const int4*>(nd + 6));
                     float d0, d1, d2, d3;
-                    int c0 = ch.x, c1 = ch.y, c2 = ch.z, c3 = ch.w;
+                    int c0, c1, c2, c3;
+                    if (!QUANT) {
+                        const float4* nd = s.nodes + (size_t)cur * 8;
+                        const float4 nxp = ldg4(nd + r.sx), fxp = ldg4(nd + (r.sx ^ 1));
+                        const float4 nyp = ldg4(nd + r.sy), fyp = ldg4(nd + (r.sy ^ 1));
+                        const float4 nzp = ldg4(nd + r.sz), fzp = ldg4(nd + (r.sz ^ 1));
+                        const int4 ch = __ldg(reinterpret_cast<const int4*>(nd + 6));
+                        c0 = ch.x; c1 = ch.y; c2 = ch.z; c3 = ch.w;
 #define ORT_BOX(k, D, C)                                                                          \
     {                                                                                             \
         const float tn = fmaxf(fmaxf(fmaf(nxp.k, r.ix, r.nx), fmaf(nyp.k, r.iy, r.ny)),           \
@@ -138,8 +147,39 @@ k_trace(const SceneDev s, const TraceArgs a) {
                                fminf(fmaf(fzp.k, r.iz, r.fz), cull));                             \
         D = (tn <= tf && C != WIDE_EMPTY) ? tn : inf;                                             \
     }
-                    ORT_BOX(x, d0, c0) ORT_BOX(y, d1, c1) ORT_BOX(z, d2, c2) ORT_BOX(w, d3, c3)
+                        ORT_BOX(x, d0, c0) ORT_BOX(y, d1, c1) ORT_BOX(z, d2, c2) ORT_BOX(w, d3, c3)
 #undef ORT_BOX
+                    } else {
+                        const uint4* nd = reinterpret_cast<const uint4*>(s.nodes) + (size_t)cur * 4;
+                        const uint4 v0 = __ldg(nd), v1 = __ldg(nd + 1), v2 = __ldg(nd + 2);
+                        const int4 ch = __ldg(reinterpret_cast<const int4*>(nd + 3));
+                        c0 = ch.x; c1 = ch.y; c2 = ch.z; c3 = ch.w;
+                        // plane = origin + q * step.  q is spliced into the mantissa of 1.0f (one PRMT):
+                        // f = 1 + q * 2^-15, so  t = f * (2^15 step / d) + ((origin - o) / d -+ pad - 2^15 step / d)
+                        const float ax_ = __uint_as_float(((v0.w & 0xffu) + 15u) << 23) * r.ix;
+                        const float ay_ = __uint_as_float((((v0.w >> 8) & 0xffu) + 15u) << 23) * r.iy;
+                        const float az_ = __uint_as_float((((v0.w >> 16) & 0xffu) + 15u) << 23) * r.iz;
+                        const float ox_ = __uint_as_float(v0.x), oy_ = __uint_as_float(v0.y), oz_ = __uint_as_float(v0.z);
+                        const float bnx = fmaf(ox_, r.ix, r.nx) - ax_, bfx = fmaf(ox_, r.ix, r.fx) - ax_;
+                        const float bny = fmaf(oy_, r.iy, r.ny) - ay_, bfy = fmaf(oy_, r.iy, r.fy) - ay_;
+                        const float bnz = fmaf(oz_, r.iz, r.nz) - az_, bfz = fmaf(oz_, r.iz, r.fz) - az_;
+                        const bool fx_ = r.sx & 1, fy_ = r.sy & 1, fz_ = r.sz & 1; // direction component negative
+                        const uint32_t nxw = fx_ ? v1.y : v1.x, fxw = fx_ ? v1.x : v1.y;
+                        const uint32_t nyw = fy_ ? v1.w : v1.z, fyw = fy_ ? v1.z : v1.w;
+                        const uint32_t nzw = fz_ ? v2.y : v2.x, fzw = fz_ ? v2.x : v2.y;
+#define ORT_QF(W, SEL) __uint_as_float(__byte_perm(W, 0x3F800000u, SEL))
+#define ORT_BOX(SEL, D, C)                                                                        \
+    {                                                                                             \
+        const float tn = fmaxf(fmaxf(fmaf(ORT_QF(nxw, SEL), ax_, bnx), fmaf(ORT_QF(nyw, SEL), ay_, bny)), \
+                               fmaxf(fmaf(ORT_QF(nzw, SEL), az_, bnz), 0.0f));                    \
+        const float tf = fminf(fminf(fmaf(ORT_QF(fxw, SEL), ax_, bfx), fmaf(ORT_QF(fyw, SEL), ay_, bfy)), \
+                               fminf(fmaf(ORT_QF(fzw, SEL), az_, bfz), cull));                    \
+        D = (tn <= tf && C != WIDE_EMPTY) ? tn : inf;                                             \
+    }
+                        ORT_BOX(0x7604u, d0, c0) ORT_BOX(0x7614u, d1, c1) ORT_BOX(0x7624u, d2, c2) ORT_BOX(0x7634u, d3, c3)
+#undef ORT_BOX
+#undef ORT_QF
+                    }
                     const int nh = (d0 < inf) + (d1 < inf) + (d2 < inf) + (d3 < inf);
                     ORT_CSWAP(d0, c0, d1, c1) ORT_CSWAP(d2, c2, d3, c3) ORT_CSWAP(d0, c0, d2, c2)
                     ORT_CSWAP(d1, c1, d3, c3) ORT_CSWAP(d1, c1, d2, c2)
@@ -155,11 +195,24 @@ k_trace(const SceneDev s, const TraceArgs a) {
                         if (nh > 2) ORT_PUSH(c2, d2)
                         if (nh > 1) ORT_PUSH(c1, d1)
                         cur = c0;
+#ifdef ORT_SPECULATE
+                        // speculative descent: park the first leaf found and keep walking inner nodes
+                        if (c0 < 0 && parked == WIDE_EMPTY && sp > 0) {
+                            parked = c0;
+                            float dd; ORT_POP(cur, dd) (void)dd;
+                        }
+#endif
                     }
                     // lanes that already hold a leaf wait at the end of this loop: once too few lanes
                     // are still descending, stop and let the waiting lanes test their triangles
                     if (__popc(__activemask()) < a.inner_min) break;
                 }
+#ifdef ORT_SPECULATE
+                if (parked != WIDE_EMPTY) { // test the parked leaf first; keep `cur` for the next round
+                    if (cur != WIDE_EMPTY) ORT_PUSH(cur, 0.0f)
+                    cur = parked; parked = WIDE_EMPTY;
+                }
+#endif
                 if (cur < 0 && cur != WIDE_EMPTY) {
                     const uint32_t code = (uint32_t)~cur;
                     const uint32_t first = code >> 3, cnt = code & 7u;

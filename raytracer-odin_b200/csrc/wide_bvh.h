@@ -61,6 +61,25 @@ struct alignas(16) TriTan { // 48 bytes
     float tan1[4], tan2[4], tan3[4];
 };
 
+// Quantised 4-wide node, 64 bytes = 4 x LDG.128 (vs 7 for WideNode).  Used for large scenes, where
+// the traversal is bound by the L1/TEX pipe (ncu: l1tex throughput 90 % on the 1 M-triangle scene).
+// Child planes are 8-bit offsets from the node's own lower corner in units of a per-axis power of
+// two: plane = origin + q * 2^(exp-127).  The quantisation is CONSERVATIVE (lower planes rounded
+// down, upper planes up, each with an extra 2^-7 step of slack for the kernel's decode rounding),
+// so the decoded boxes contain the reference's boxes: supersets cannot change the closest hit.
+//   bytes  0..11 origin.xyz (f32)   12..15 exp.x | exp.y << 8 | exp.z << 16
+//         16..19 lo.x[4 children]   20..23 hi.x[4]   24..27 lo.y[4]   28..31 hi.y[4]
+//         32..35 lo.z[4]            36..39 hi.z[4]   40..47 reserved
+//         48..63 child[4]   (same encoding as WideNode)
+struct alignas(16) QuantNode {
+    float origin[3];
+    uint32_t exps;
+    uint32_t planes[3][2]; // [axis][lo|hi], byte k = child k
+    uint32_t reserved[2];
+    int32_t child[4];
+};
+static_assert(sizeof(QuantNode) == 64, "QuantNode must be half a cache line");
+
 struct WideBVH {
     std::vector<WideNode> nodes; // root = 0
     int depth = 0;               // wide levels, root = 1
@@ -71,6 +90,9 @@ struct WideBVH {
 // Re-emit the reference's binary post-order BVH (root = last node, raytracer.odin:375) as a
 // 4-wide BVH.  Returns false (with *err set) on malformed input.
 bool build_wide_bvh(const ort_bvh_node* bvh, int64_t n_nodes, int64_t n_tris, WideBVH* out, const char** err);
+
+// Conservative 8-bit re-encoding of a WideNode array (same indices, same children).
+void quantize_wide_nodes(const WideNode* in, size_t n, QuantNode* out);
 
 void make_isect_records(const ort_triangle* tris, int64_t n, TriIsect* out);
 void make_light_records(const ort_triangle* tris, int64_t n, TriLight* out);

@@ -63,6 +63,11 @@ def scenes(scene_dir):
             env = scenegen.write_env_hdr(os.path.join(d, "env.hdr"), 64, 32, sun_peak=50.0)
         elif name == "spheres_c2":
             p = scenegen.spheres(os.path.join(d, "s.gltf"))
+        elif name == "terrain_c4":
+            p = scenegen.terrain(os.path.join(d, "s.gltf"))
+        elif name == "textured_c3":
+            p = scenegen.textured(os.path.join(d, "s.gltf"))
+            env = scenegen.write_env_hdr(os.path.join(d, "env.hdr"), 2048, 1024)
         elif name == "terrain_small":
             p = scenegen.terrain(os.path.join(d, "s.gltf"), grid=48, n_spheres=24, subdiv=2, seed=3, n_emissive=3)
         elif name == "textured_small":
@@ -70,7 +75,10 @@ def scenes(scene_dir):
             env = scenegen.write_env_hdr(os.path.join(d, "env.hdr"), 128, 64)
         else:
             raise KeyError(name)
-        cache[key] = _load(p, w, h, orc.bvh_build, env)
+        from raytracer_odin_b200.scene import native_bvh_build
+
+        # the two builders are tested equal (tests/test_host.py); the big scenes use the faster one
+        cache[key] = _load(p, w, h, native_bvh_build if name.endswith(("_c4", "_c3", "_c2")) else orc.bvh_build, env)
         return cache[key]
 
     return get

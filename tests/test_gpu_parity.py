@@ -239,3 +239,47 @@ def test_full_size_c2_primary_hits(scenes, orc):
     n_ties = _hits_equal(g, ref, "C2 1080p", o.ties)
     print(f"C2 1080p: {len(ref)} primary rays, {n_ties} exact-t ties, all tie-free rays bit-identical")
     assert c["stack_drops"] == 0
+
+
+def test_full_size_c4_subsampled_hits_and_split(scenes, orc):
+    """BASELINE config 4 at full size (1920x1080, ~1.0 M triangles): 300k of the GPU's own primary
+    rays re-traced by the faithful oracle must agree bit for bit (tie-free rays), the stack never
+    overflows, and rendering in many small waves gives the same sums as one big wave."""
+    w, h = 1920, 1080
+    scene = scenes("terrain_c4", w, h)
+    assert len(scene.triangles) > 1_000_000
+    o = orc.OracleScene(scene)
+    with _renderer(scene) as r:
+        g, rays = r.primary_hits(w, h, 5, want_rays=True)
+        pick = np.random.default_rng(2).choice(w * h, 300_000, replace=False)
+        ref, c = o.trace_rays(rays[pick], mode=0, threads=orc.load().orc_hardware_threads())
+        n_ties = _hits_equal(g[pick], ref, "C4 1080p", o.ties, max_tie_frac=1e-4)
+        assert c["stack_drops"] == 0, c
+        a = r.render(w, h, 10, 2)
+        st = r.stats()
+    with _renderer(scene, max_paths_in_flight=w * h) as r2:
+        b = r2.render(w, h, 10, 2)
+    assert np.array_equal(a["count"], b["count"])
+    np.testing.assert_allclose(a["total"], b["total"], rtol=1e-5, atol=1e-6)
+    assert st["wide_depth"] < 40 and np.isfinite(a["total"]).all()
+    print(f"C4: {n_ties} ties in 300k rays; reference stack high-water {c['stack_high']}; wide depth {st['wide_depth']}")
+
+
+def test_full_size_c3_window_radiance(scenes, orc):
+    """BASELINE config 3 (textured metallic-roughness + normal maps + HDR env map) at 1920x1080:
+    a 160x90 window rendered by the oracle with the same streams; relRMSE <= 1e-2, luminance 0.5 %."""
+    from raytracer_odin_b200 import api
+
+    w, h, depth, spp = 1920, 1080, 8, 4
+    scene = scenes("textured_c3", w, h)
+    win = (880, 495, 1040, 585)
+    with _renderer(scene) as r:
+        px = r.render(w, h, depth, spp)
+    opx, _ = orc.OracleScene(scene).render(w, h, depth, spp, seed=SEED, mode=1, schedule=1,
+                                           threads=orc.load().orc_hardware_threads(), window=win)
+    m = opx["count"] > 0
+    assert m.sum() == 160 * 90
+    a = (px["total"][m] / spp).reshape(1, -1, 3)
+    b = (opx["total"][m] / spp).reshape(1, -1, 3)
+    rmse, lum = api.rel_rmse(a, b)
+    assert rmse <= 1e-2 and abs(lum - 1) <= 5e-3, (rmse, lum)

@@ -6,11 +6,12 @@ rep, kname, skip = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 45
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = sys.argv[5] if len(sys.argv) > 5 else os.path.join(ROOT, "raytracer-odin_b200/csrc/libodinrt_b200.so")
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", f"regex:{kname}",
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", f"regex:{kname.split(chr(58))[0]}",
                       "--launch-skip", skip, "--launch-count", "1"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hi = next(i for i, r in enumerate(rows) if "Source" in r and "Instructions Executed" in r)
 hdr, data = rows[hi], [r for r in rows[hi + 1:] if len(r) == len(rows[hi])]
+data = data[::2] if len(data) > 1 and data[0] == data[1] else data  # ncu prints every SASS row twice
 ix = {h: i for i, h in enumerate(hdr)}
 def f(r, k):
     try: return float(r[ix[k]])
