@@ -218,6 +218,24 @@ int  ort_reset_stats(ort_ctx* ctx);
 /* When on, render calls time each kernel class with CUDA events (serialises the pipeline). */
 int  ort_set_profiling(ort_ctx* ctx, int32_t on);
 
+/* ---- several GPUs of one box from ONE host process (the Odin host is a single process) ------
+ * Every listed device holds a full scene replica and renders a contiguous block of the sample
+ * range (counter-based RNG keyed by the global sample index: any split renders the same sample
+ * set).  The partial accumulators are combined once per call by a reduce kernel on devices[0]
+ * that reads the other GPUs' accumulators directly through NVLink peer memory (staged
+ * cudaMemcpyPeer when peer access is unavailable), then merged into `out` like ort_render.
+ * The reference's analogue is its thread pool pulling tasks from one atomic counter
+ * (raytracer.odin:551,609-623). */
+typedef struct ort_multi ort_multi;
+int  ort_multi_create(ort_multi** out, const int32_t* devices, int32_t n_devices, uint64_t seed);
+void ort_multi_destroy(ort_multi* m);
+const char* ort_multi_last_error(const ort_multi* m); /* m may be NULL: last error of ort_multi_create */
+int  ort_multi_upload_scene(ort_multi* m, const ort_scene* scene);
+int  ort_multi_render(ort_multi* m, uint32_t w, uint32_t h, int32_t ray_depth,
+                      uint64_t first_sample, uint64_t n_samples,
+                      ort_sample_stats* out, const volatile uint8_t* interrupt);
+int  ort_multi_get_stats(ort_multi* m, ort_stats* out); /* counters summed, times = max over devices */
+
 /* Host-side scene finalisation helper (NOT used when Odin is the host): the reference
  * bvh_build (raytracer.odin:227-342) as native code, for hosts that do not have one.
  * Sorts `tris` in place like the reference; writes up to `cap` nodes, returns node count

@@ -155,6 +155,58 @@ class Renderer:
         self._check(self.lib.ort_reset_stats(self._ctx))
 
 
+class MultiRenderer:
+    """Several GPUs of one box driven from this one process (ort_multi_*): full scene replica per
+    GPU, contiguous sample blocks, one peer-memory reduce per render call."""
+
+    def __init__(self, devices, seed: int = 0):
+        self.lib = cabi.load_library()
+        self._m = C.c_void_p()
+        devs = (C.c_int32 * len(devices))(*devices)
+        if self.lib.ort_multi_create(C.byref(self._m), devs, len(devices), seed) != 0:
+            raise OrtError(self.lib.ort_multi_last_error(None).decode())
+        self.devices = list(devices)
+
+    def close(self):
+        if self._m:
+            self.lib.ort_multi_destroy(self._m)
+            self._m = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise OrtError(self.lib.ort_multi_last_error(self._m).decode())
+
+    def upload_scene(self, scene: Scene):
+        cs, keep = scene.to_c()
+        self._check(self.lib.ort_multi_upload_scene(self._m, C.byref(cs)))
+        return self
+
+    def render(self, width, height, ray_depth, n_samples, first_sample=0, out=None, interrupt=None):
+        if out is None:
+            out = np.zeros(width * height, cabi.STATS_DTYPE)
+        iptr = interrupt.ctypes.data_as(C.c_void_p) if interrupt is not None else None
+        self._check(self.lib.ort_multi_render(self._m, width, height, ray_depth, first_sample, n_samples,
+                                              cabi.ptr(out), iptr))
+        return out
+
+    def stats(self) -> dict:
+        s = cabi.OrtStats()
+        self._check(self.lib.ort_multi_get_stats(self._m, C.byref(s)))
+        return s.as_dict()
+
+
 def mean_image(stats: np.ndarray, width: int, height: int) -> np.ndarray:
     """Linear mean radiance (total / count), image row order (row 0 = top)."""
     cnt = np.maximum(stats["count"].astype(np.float32), 1)[:, None]

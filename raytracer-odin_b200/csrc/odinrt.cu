@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "kernels.cuh"
@@ -340,6 +341,30 @@ int render_impl(ort_ctx* ctx, uint32_t w, uint32_t h, int32_t depth, uint64_t fi
     return 0;
 }
 
+
+// Device accumulators (+ first / last planes) -> packed Sample_Stats -> pinned host -> merged into
+// `out` like repeated rc_set_pixel calls would (main.odin:96-101).
+int pack_and_merge(ort_ctx* ctx, const float* accum, const float* first, const float* last, size_t npix,
+                   uint32_t* packed, ort_sample_stats* out) {
+    k_pack_stats<<<ctx->shade_grid, 256, 0, ctx->stream>>>(accum, first, last, (uint32_t)npix, packed);
+    ctx->launches++;
+    if (ensure_pinned(ctx, npix * 52)) return 1;
+    CK(cudaMemcpyAsync(ctx->pinned, packed, npix * 52, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->ms_render = ms; else cudaGetLastError();
+    const ort_sample_stats* src = (const ort_sample_stats*)ctx->pinned;
+    for (size_t i = 0; i < npix; i++) {
+        if (src[i].count == 0) continue;
+        ort_sample_stats& d = out[i];
+        if (d.count == 0) std::memcpy(d.first, src[i].first, 12);
+        d.count += src[i].count;
+        std::memcpy(d.last, src[i].last, 12);
+        for (int c = 0; c < 3; c++) { d.total[c] += src[i].total[c]; d.total_squared[c] += src[i].total_squared[c]; }
+    }
+    return 0;
+}
+
 } // namespace
 
 // =================================================================================================
@@ -471,9 +496,10 @@ int ort_upload_scene(ort_ctx* ctx, const ort_scene* sc) {
         }
         if ((uint64_t)sc->n_triangles + (uint64_t)sc->n_light_triangles >= (1u << 28))
             return fail(ctx, "ort_upload_scene: more than 2^28 traversal triangles");
-        // node encoding: f32 planes for small trees (issue bound), 8-bit planes for large ones
-        // (L1/TEX bound) — see traverse.cuh; ORT_QUANT=0/1 forces one (tuning / tests)
-        ctx->quant = nodes.size() * sizeof(WideNode) > ((size_t)48 << 20); // beyond ~L2/2 the smaller nodes win on capacity
+        // node encoding: f32 planes by default.  The 8-bit encoding (QuantNode) halves the node
+        // traffic but its decode ALU cancels the gain on every scene measured so far (C2, C4, C5:
+        // profiles/r1_traversal_variants.md), so it is opt-in: ORT_QUANT=1
+        ctx->quant = false;
         if (const char* e2 = std::getenv("ORT_QUANT")) ctx->quant = std::atoi(e2) != 0;
         if (ctx->quant) {
             std::vector<QuantNode> qn(nodes.size());
@@ -595,25 +621,7 @@ int ort_render(ort_ctx* ctx, uint32_t w, uint32_t h, int32_t ray_depth, uint64_t
     CK(cudaMemsetAsync(accum, 0, npix * 14 * 4, ctx->stream));
     uint64_t done = 0;
     if (render_impl(ctx, w, h, ray_depth, first_sample, n_samples, accum, first, last, interrupt, &done)) return 1;
-    k_pack_stats<<<ctx->shade_grid, 256, 0, ctx->stream>>>(accum, first, last, (uint32_t)npix, packed);
-    ctx->launches++;
-    if (ensure_pinned(ctx, npix * 52)) return 1;
-    CK(cudaMemcpyAsync(ctx->pinned, packed, npix * 52, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    float ms = 0;
-    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
-    ctx->ms_render = ms;
-    // merge like repeated rc_set_pixel calls would (main.odin:96-101)
-    const ort_sample_stats* src = (const ort_sample_stats*)ctx->pinned;
-    for (size_t i = 0; i < npix; i++) {
-        if (src[i].count == 0) continue;
-        ort_sample_stats& d = out[i];
-        if (d.count == 0) std::memcpy(d.first, src[i].first, 12);
-        d.count += src[i].count;
-        std::memcpy(d.last, src[i].last, 12);
-        for (int c = 0; c < 3; c++) { d.total[c] += src[i].total[c]; d.total_squared[c] += src[i].total_squared[c]; }
-    }
-    return 0;
+    return pack_and_merge(ctx, accum, first, last, npix, packed, out);
 }
 
 int ort_unpack_accum(ort_ctx* ctx, uint32_t w, uint32_t h, const float* d_accum, ort_sample_stats* out) {
@@ -762,6 +770,179 @@ int ort_reset_stats(ort_ctx* ctx) {
     CK(cudaMemset(ctx->d_stats, 0, 8 * sizeof(unsigned long long)));
     ctx->ms_trace = ctx->ms_light = ctx->ms_shade = ctx->ms_other = ctx->ms_render = 0;
     ctx->launches = 0;
+    return 0;
+}
+
+} // extern "C"
+
+// =================================================================================================
+// Several GPUs from one process: sample-index split + one peer-memory reduce per call.
+// =================================================================================================
+struct ort_multi {
+    std::vector<ort_ctx*> ctx;
+    std::vector<char> peer; // devices[0] can dereference ctx[g]'s memory directly
+    std::string err;
+};
+
+namespace {
+thread_local std::string g_multi_create_error;
+
+struct PeerPtrs {
+    const float* p[16];
+};
+// dst[i] += sum over peers; 7 planes (total, total_squared, count) of npix floats each.
+__global__ void k_reduce_peers(float* __restrict__ dst, const PeerPtrs peers, const int n_peers, const size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float acc = dst[i];
+        for (int k = 0; k < n_peers; k++) acc += peers.p[k][i]; // NVLink peer loads (or the local staging copy)
+        dst[i] = acc;
+    }
+}
+int mfail(ort_multi* m, const std::string& msg) {
+    if (m) m->err = msg; else g_multi_create_error = msg;
+    return 1;
+}
+} // namespace
+
+extern "C" {
+
+const char* ort_multi_last_error(const ort_multi* m) { return m ? m->err.c_str() : g_multi_create_error.c_str(); }
+
+void ort_multi_destroy(ort_multi* m) {
+    if (!m) return;
+    for (ort_ctx* c : m->ctx) ort_destroy(c);
+    delete m;
+}
+
+int ort_multi_create(ort_multi** out, const int32_t* devices, int32_t n_devices, uint64_t seed) {
+    if (!out || !devices || n_devices < 1 || n_devices > 16) return mfail(nullptr, "ort_multi_create: need 1..16 devices");
+    *out = nullptr;
+    ort_multi* m = new ort_multi();
+    for (int g = 0; g < n_devices; g++) {
+        ort_device_cfg cfg{};
+        cfg.device = devices[g];
+        cfg.seed = seed;
+        ort_ctx* c = nullptr;
+        if (ort_create(&c, &cfg) != 0) {
+            g_multi_create_error = std::string("device ") + std::to_string(devices[g]) + ": " + ort_last_error(nullptr);
+            ort_multi_destroy(m);
+            return 1;
+        }
+        m->ctx.push_back(c);
+    }
+    m->peer.assign((size_t)n_devices, 0);
+    m->peer[0] = 1;
+    for (int g = 1; g < n_devices; g++) {
+        if (m->ctx[g]->device == m->ctx[0]->device) { m->peer[g] = 1; continue; }
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, m->ctx[0]->device, m->ctx[g]->device);
+        if (can) {
+            Bind b(m->ctx[0]->device);
+            cudaError_t e = cudaDeviceEnablePeerAccess(m->ctx[g]->device, 0);
+            if (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled) m->peer[g] = 1;
+            cudaGetLastError();
+        }
+    }
+    *out = m;
+    return 0;
+}
+
+int ort_multi_upload_scene(ort_multi* m, const ort_scene* scene) {
+    if (!m) return 1;
+    for (size_t g = 0; g < m->ctx.size(); g++)
+        if (ort_upload_scene(m->ctx[g], scene) != 0)
+            return mfail(m, "device " + std::to_string(m->ctx[g]->device) + ": " + ort_last_error(m->ctx[g]));
+    return 0;
+}
+
+int ort_multi_render(ort_multi* m, uint32_t w, uint32_t h, int32_t ray_depth, uint64_t first_sample,
+                     uint64_t n_samples, ort_sample_stats* out, const volatile uint8_t* interrupt) {
+    if (!m) return 1;
+    if (!out) return mfail(m, "ort_multi_render: out is NULL");
+    const int G = (int)m->ctx.size();
+    const size_t npix = (size_t)w * h;
+    // contiguous sample blocks, sizes differ by at most one
+    std::vector<uint64_t> first((size_t)G), cnt((size_t)G);
+    {
+        const uint64_t base = n_samples / (uint64_t)G, rem = n_samples % (uint64_t)G;
+        uint64_t f = first_sample;
+        for (int g = 0; g < G; g++) { cnt[g] = base + ((uint64_t)g < rem ? 1 : 0); first[g] = f; f += cnt[g]; }
+    }
+    int last_g = 0;
+    for (int g = 0; g < G; g++) if (cnt[g] > 0) last_g = g;
+    std::vector<int> rc((size_t)G, 0);
+    auto work = [&](int g) {
+        ort_ctx* ctx = m->ctx[g];
+        Bind b(ctx->device);
+        auto body = [&]() -> int {
+            // planes: 8 accum + 3 first + 3 last (+ packed Sample_Stats and a staging area on device 0)
+            if (ensure_scratch(ctx, npix * (14 * 4 + 52) + (g == 0 ? npix * 7 * 4 : 0))) return 1;
+            float* accum = ctx->scratch;
+            CK(cudaMemsetAsync(accum, 0, npix * 14 * 4, ctx->stream));
+            if (cnt[g] > 0 &&
+                render_impl(ctx, w, h, ray_depth, first[g], cnt[g], accum, g == 0 ? accum + 8 * npix : nullptr,
+                            g == last_g ? accum + 11 * npix : nullptr, interrupt, nullptr))
+                return 1;
+            CK(cudaStreamSynchronize(ctx->stream));
+            return 0;
+        };
+        rc[g] = body();
+    };
+    std::vector<std::thread> pool;
+    for (int g = 1; g < G; g++) pool.emplace_back(work, g);
+    work(0);
+    for (auto& t : pool) t.join();
+    for (int g = 0; g < G; g++)
+        if (rc[g]) return mfail(m, "device " + std::to_string(m->ctx[g]->device) + ": " + ort_last_error(m->ctx[g]));
+
+    ort_ctx* ctx = m->ctx[0];
+    Bind b(ctx->device);
+    float* accum = ctx->scratch;
+    float* firstp = accum + 8 * npix;
+    float* lastp = firstp + 3 * npix;
+    uint32_t* packed = (uint32_t*)(lastp + 3 * npix);
+    float* staging = (float*)((char*)packed + npix * 52);
+    // the one reduce of the frame: devices[0] sums its peers' accumulators
+    PeerPtrs pp{};
+    int np = 0;
+    for (int g = 1; g < G; g++) {
+        if (cnt[g] == 0) continue;
+        if (m->peer[g]) {
+            pp.p[np++] = m->ctx[g]->scratch;
+        } else { // no peer access: stage, add, repeat
+            CK(cudaMemcpyPeerAsync(staging, ctx->device, m->ctx[g]->scratch, m->ctx[g]->device, npix * 7 * 4, ctx->stream));
+            PeerPtrs one{};
+            one.p[0] = staging;
+            k_reduce_peers<<<ctx->shade_grid, 256, 0, ctx->stream>>>(accum, one, 1, npix * 7);
+            ctx->launches++;
+        }
+    }
+    if (np > 0) {
+        k_reduce_peers<<<ctx->shade_grid, 256, 0, ctx->stream>>>(accum, pp, np, npix * 7);
+        ctx->launches++;
+    }
+    if (last_g != 0)
+        CK(cudaMemcpyPeerAsync(lastp, ctx->device, m->ctx[last_g]->scratch + 11 * npix, m->ctx[last_g]->device,
+                               npix * 3 * 4, ctx->stream));
+    CK(cudaGetLastError());
+    if (pack_and_merge(ctx, accum, firstp, lastp, npix, packed, out)) return mfail(m, ort_last_error(ctx));
+    return 0;
+}
+
+int ort_multi_get_stats(ort_multi* m, ort_stats* out) {
+    if (!m || !out) return 1;
+    std::memset(out, 0, sizeof *out);
+    for (size_t g = 0; g < m->ctx.size(); g++) {
+        ort_stats s;
+        if (ort_get_stats(m->ctx[g], &s)) return mfail(m, ort_last_error(m->ctx[g]));
+        out->rays_closest += s.rays_closest; out->rays_traced += s.rays_traced; out->rays_light_pdf += s.rays_light_pdf;
+        out->paths += s.paths; out->kernel_launches += s.kernel_launches;
+        out->render_ms = std::max(out->render_ms, s.render_ms);
+        out->trace_ms = std::max(out->trace_ms, s.trace_ms); out->light_ms = std::max(out->light_ms, s.light_ms);
+        out->shade_ms = std::max(out->shade_ms, s.shade_ms); out->other_ms = std::max(out->other_ms, s.other_ms);
+        out->wide_nodes = s.wide_nodes; out->wide_depth = s.wide_depth; out->light_wide_nodes = s.light_wide_nodes;
+        out->device_bytes += s.device_bytes;
+    }
     return 0;
 }
 

@@ -283,3 +283,31 @@ def test_full_size_c3_window_radiance(scenes, orc):
     b = (opx["total"][m] / spp).reshape(1, -1, 3)
     rmse, lum = api.rel_rmse(a, b)
     assert rmse <= 1e-2 and abs(lum - 1) <= 5e-3, (rmse, lum)
+
+
+def test_multi_device_library_split(scenes):
+    """ort_multi_*: sample split + one peer reduce from a single process.  With one physical GPU the
+    two contexts share it (devices=[0, 0]); with two or more, real NVLink peers are used.  The sum
+    over the blocks equals the single-context render up to f32 summation order, first/last are
+    those of the first / last sample, and the ray count is identical."""
+    import torch
+
+    from raytracer_odin_b200 import api
+
+    scene = scenes("spheres_small", 96, 54)
+    w, h, depth, spp = 96, 54, 6, 9
+    with _renderer(scene) as r:
+        one = r.render(w, h, depth, spp)
+        rays_one = r.stats()["rays_closest"]
+    n = torch.cuda.device_count()
+    for devices in ([0], [0, 0], [0, 0, 0, 0]) + (([0, 1],) if n >= 2 else ()) + ((list(range(n)),) if n > 2 else ()):
+        with api.MultiRenderer(devices, seed=SEED).upload_scene(scene) as m:
+            got = m.render(w, h, depth, spp)
+            st = m.stats()
+        assert np.array_equal(got["count"], one["count"]), devices
+        np.testing.assert_allclose(got["total"], one["total"], rtol=1e-5, atol=1e-6, err_msg=str(devices))
+        np.testing.assert_allclose(got["total_squared"], one["total_squared"], rtol=1e-5, atol=1e-5)
+        assert np.array_equal(got["first"], one["first"]) and np.array_equal(got["last"], one["last"]), devices
+        assert st["rays_closest"] == rays_one, devices
+    with pytest.raises(api.OrtError):
+        api.MultiRenderer([0, 99])
