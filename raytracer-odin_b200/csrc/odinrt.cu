@@ -22,6 +22,8 @@ namespace {
 thread_local std::string g_create_error;
 }
 
+constexpr int MAX_PIPES = 8;
+
 struct ort_ctx {
     int device = 0;
     int sm_count = 148;
@@ -41,14 +43,20 @@ struct ort_ctx {
     WideBVH wide, lwide;
     int64_t scene_bytes = 0;
 
-    // path buffers (one wave)
-    int64_t capacity = 0;
-    float4 *qo[2] = {nullptr, nullptr}, *qd[2] = {nullptr, nullptr};
-    float4* hits = nullptr;
-    float* lsum = nullptr;
-    float4 *st_a = nullptr, *st_b = nullptr, *st_c = nullptr;
-    uint32_t* counters = nullptr; // 4 arrays of D+2: queue counts, trace work counters, light work counters, used-ray counts
-    int counters_depth = 0;
+    // path buffers: two independent wave pipelines (ps[1] only when waves are overlapped)
+    struct PathSet {
+        float4 *qo[2] = {nullptr, nullptr}, *qd[2] = {nullptr, nullptr};
+        float4* hits = nullptr;
+        float* lsum = nullptr;
+        float4 *st_a = nullptr, *st_b = nullptr, *st_c = nullptr;
+        uint32_t* counters = nullptr; // 4 arrays of D+2: queue counts, trace work counters, light work counters, used-ray counts
+        int64_t capacity = 0;
+        int counters_depth = 0;
+        cudaEvent_t resolved = nullptr; // recorded after this pipeline's k_resolve + k_stats
+    } ps[MAX_PIPES];
+    cudaStream_t aux_stream[MAX_PIPES] = {}; // pipelines 1.. (0 runs on `stream`)
+    cudaEvent_t ev_fork = nullptr, ev_join[MAX_PIPES] = {};
+    int overlap = 4;                    // number of overlapped wave pipelines (env ORT_OVERLAP=1..4)
     unsigned long long* d_stats = nullptr;
     int64_t path_bytes = 0;
 
@@ -98,11 +106,13 @@ void free_scene(ort_ctx* c) {
     c->scene_bytes = 0;
 }
 void free_paths(ort_ctx* c) {
-    void* ptrs[] = {c->qo[0], c->qo[1], c->qd[0], c->qd[1], c->hits, c->lsum, c->st_a, c->st_b, c->st_c};
-    for (void* p : ptrs) if (p) cudaFree(p);
-    c->qo[0] = c->qo[1] = c->qd[0] = c->qd[1] = c->hits = c->st_a = c->st_b = c->st_c = nullptr;
-    c->lsum = nullptr;
-    c->capacity = 0;
+    for (auto& P : c->ps) {
+        void* ptrs[] = {P.qo[0], P.qo[1], P.qd[0], P.qd[1], P.hits, P.lsum, P.st_a, P.st_b, P.st_c};
+        for (void* p : ptrs) if (p) cudaFree(p);
+        P.qo[0] = P.qo[1] = P.qd[0] = P.qd[1] = P.hits = P.st_a = P.st_b = P.st_c = nullptr;
+        P.lsum = nullptr;
+        P.capacity = 0;
+    }
     c->path_bytes = 0;
 }
 
@@ -170,29 +180,38 @@ int make_texture(ort_ctx* ctx, const ort_texture& t, bool srgb, cudaTextureObjec
     return 0;
 }
 
-int ensure_paths(ort_ctx* ctx, int64_t need) {
-    if (ctx->capacity >= need) return 0;
-    free_paths(ctx);
-    const size_t n = (size_t)need;
-    for (int i = 0; i < 2; i++) {
-        CK(cudaMalloc(&ctx->qo[i], n * 16));
-        CK(cudaMalloc(&ctx->qd[i], n * 16));
+int ensure_paths(ort_ctx* ctx, int64_t need, int pipes = 1) {
+    for (int i = 0; i < pipes; i++) {
+        auto& P = ctx->ps[i];
+        if (P.capacity >= need) continue;
+        void* ptrs[] = {P.qo[0], P.qo[1], P.qd[0], P.qd[1], P.hits, P.lsum, P.st_a, P.st_b, P.st_c};
+        for (void* p : ptrs) if (p) cudaFree(p);
+        ctx->path_bytes -= P.capacity * (16 * 8 + 4);
+        P.capacity = 0;
+        const size_t n = (size_t)need;
+        for (int k = 0; k < 2; k++) {
+            CK(cudaMalloc(&P.qo[k], n * 16));
+            CK(cudaMalloc(&P.qd[k], n * 16));
+        }
+        CK(cudaMalloc(&P.hits, n * 16));
+        CK(cudaMalloc(&P.lsum, n * 4));
+        CK(cudaMalloc(&P.st_a, n * 16));
+        CK(cudaMalloc(&P.st_b, n * 16));
+        CK(cudaMalloc(&P.st_c, n * 16));
+        P.capacity = need;
+        ctx->path_bytes += (int64_t)(n * (16 * 8 + 4));
     }
-    CK(cudaMalloc(&ctx->hits, n * 16));
-    CK(cudaMalloc(&ctx->lsum, n * 4));
-    CK(cudaMalloc(&ctx->st_a, n * 16));
-    CK(cudaMalloc(&ctx->st_b, n * 16));
-    CK(cudaMalloc(&ctx->st_c, n * 16));
-    ctx->capacity = need;
-    ctx->path_bytes = (int64_t)(n * (16 * 8 + 4));
     return 0;
 }
-int ensure_counters(ort_ctx* ctx, int depth) {
-    if (ctx->counters && ctx->counters_depth >= depth) return 0;
-    if (ctx->counters) cudaFree(ctx->counters);
-    ctx->counters = nullptr;
-    CK(cudaMalloc(&ctx->counters, sizeof(uint32_t) * 4 * (size_t)(depth + 2)));
-    ctx->counters_depth = depth;
+int ensure_counters(ort_ctx* ctx, int depth, int pipes = 1) {
+    for (int i = 0; i < pipes; i++) {
+        auto& P = ctx->ps[i];
+        if (P.counters && P.counters_depth >= depth) continue;
+        if (P.counters) cudaFree(P.counters);
+        P.counters = nullptr;
+        CK(cudaMalloc(&P.counters, sizeof(uint32_t) * 4 * (size_t)(depth + 2)));
+        P.counters_depth = depth;
+    }
     return 0;
 }
 int ensure_scratch(ort_ctx* ctx, size_t bytes) {
@@ -213,25 +232,26 @@ int ensure_pinned(ort_ctx* ctx, size_t bytes) {
 }
 
 // mode 0: closest hit, 1: light-pdf sum, 2: both fused in one pass
-void launch_trace(ort_ctx* ctx, const float4* qo, const float4* qd, const uint32_t* n_ptr, uint32_t* work_ctr, int mode) {
+void launch_trace(ort_ctx* ctx, ort_ctx::PathSet& P, cudaStream_t st, const float4* qo, const float4* qd,
+                  const uint32_t* n_ptr, uint32_t* work_ctr, int mode) {
     TraceArgs a;
     a.qo = qo; a.qd = qd; a.n_ptr = n_ptr; a.work_ctr = work_ctr;
-    a.hits = ctx->hits; a.lsum = ctx->lsum;
+    a.hits = P.hits; a.lsum = P.lsum;
     a.refill_threshold = ctx->refill; a.inner_min = ctx->inner_min;
     const int g = ctx->trace_grid[ctx->quant ? 1 : 0][mode];
     if (!ctx->quant) {
-        if (mode == 0) k_trace<true, false, false><<<g, TRACE_THREADS, 0, ctx->stream>>>(ctx->sd, a);
-        else if (mode == 1) k_trace<false, true, false><<<g, TRACE_THREADS, 0, ctx->stream>>>(ctx->sd, a);
-        else k_trace<true, true, false><<<g, TRACE_THREADS, 0, ctx->stream>>>(ctx->sd, a);
+        if (mode == 0) k_trace<true, false, false><<<g, TRACE_THREADS, 0, st>>>(ctx->sd, a);
+        else if (mode == 1) k_trace<false, true, false><<<g, TRACE_THREADS, 0, st>>>(ctx->sd, a);
+        else k_trace<true, true, false><<<g, TRACE_THREADS, 0, st>>>(ctx->sd, a);
     } else {
-        if (mode == 0) k_trace<true, false, true><<<g, TRACE_THREADS, 0, ctx->stream>>>(ctx->sd, a);
-        else if (mode == 1) k_trace<false, true, true><<<g, TRACE_THREADS, 0, ctx->stream>>>(ctx->sd, a);
-        else k_trace<true, true, true><<<g, TRACE_THREADS, 0, ctx->stream>>>(ctx->sd, a);
+        if (mode == 0) k_trace<true, false, true><<<g, TRACE_THREADS, 0, st>>>(ctx->sd, a);
+        else if (mode == 1) k_trace<false, true, true><<<g, TRACE_THREADS, 0, st>>>(ctx->sd, a);
+        else k_trace<true, true, true><<<g, TRACE_THREADS, 0, st>>>(ctx->sd, a);
     }
     ctx->launches++;
 }
 
-struct Prof {
+struct Prof { // profiling runs single-pipeline on ctx->stream
     ort_ctx* c;
     double* acc;
     Prof(ort_ctx* ctx, double* a) : c(ctx), acc(a) { if (c->profiling) cudaEventRecord(c->evp0, c->stream); }
@@ -258,20 +278,20 @@ void fill_params(ort_ctx* ctx, uint32_t w, uint32_t h, int32_t depth, RenderPara
     p->sample_base = 0;
 }
 
-// One wave: n_batch_samples samples of every pixel, all bounces, then accumulation.
-int launch_wave(ort_ctx* ctx, const RenderParams& p, float* d_accum, float* d_first, float* d_last, int write_first,
-                int write_last) {
+// One wave: n_batch_samples samples of every pixel, all bounces, then accumulation.  `wait_for` is
+// the previous wave's `resolved` event (other pipeline): accumulation stays in wave order.
+int launch_wave(ort_ctx* ctx, ort_ctx::PathSet& P, cudaStream_t st, cudaEvent_t wait_for, const RenderParams& p,
+                float* d_accum, float* d_first, float* d_last, int write_first, int write_last) {
     const int D = p.ray_depth;
-    uint32_t* counts = ctx->counters;
-    uint32_t* wtrace = ctx->counters + (D + 2);
-    uint32_t* wlight = ctx->counters + 2 * (D + 2);
-    uint32_t* used = ctx->counters + 3 * (D + 2);
-    cudaStream_t st = ctx->stream;
+    uint32_t* counts = P.counters;
+    uint32_t* wtrace = P.counters + (D + 2);
+    uint32_t* wlight = P.counters + 2 * (D + 2);
+    uint32_t* used = P.counters + 3 * (D + 2);
     const bool lights = ctx->sd.n_lights > 0;
     {
         Prof pr(ctx, &ctx->ms_other);
-        CK(cudaMemsetAsync(ctx->counters, 0, sizeof(uint32_t) * 4 * (size_t)(D + 2), st));
-        k_raygen<<<ctx->shade_grid, 256, 0, st>>>(p, ctx->qo[0], ctx->qd[0], counts);
+        CK(cudaMemsetAsync(P.counters, 0, sizeof(uint32_t) * 4 * (size_t)(D + 2), st));
+        k_raygen<<<ctx->shade_grid, 256, 0, st>>>(p, P.qo[0], P.qd[0], counts);
         ctx->launches++;
     }
     for (int k = 0; k < D; k++) {
@@ -279,24 +299,26 @@ int launch_wave(ort_ctx* ctx, const RenderParams& p, float* d_accum, float* d_fi
         const bool need_light = k > 0 && lights; // bounce 0 has no pending pdf to complete
         {
             Prof pr(ctx, &ctx->ms_trace);
-            launch_trace(ctx, ctx->qo[in], ctx->qd[in], counts + k, wtrace + k, (need_light && ctx->fuse) ? 2 : 0);
+            launch_trace(ctx, P, st, P.qo[in], P.qd[in], counts + k, wtrace + k, (need_light && ctx->fuse) ? 2 : 0);
         }
         if (need_light && !ctx->fuse) {
             Prof pr(ctx, &ctx->ms_light);
-            launch_trace(ctx, ctx->qo[in], ctx->qd[in], counts + k, wlight + k, 1);
+            launch_trace(ctx, P, st, P.qo[in], P.qd[in], counts + k, wlight + k, 1);
         }
         {
             Prof pr(ctx, &ctx->ms_shade);
-            k_shade<<<ctx->shade_grid, 256, 0, st>>>(ctx->sd, p, k, ctx->qo[in], ctx->qd[in], ctx->hits, ctx->lsum, counts + k,
-                                                     ctx->qo[out], ctx->qd[out], counts + k + 1, used + k, ctx->st_a, ctx->st_b, ctx->st_c);
+            k_shade<<<ctx->shade_grid, 256, 0, st>>>(ctx->sd, p, k, P.qo[in], P.qd[in], P.hits, P.lsum, counts + k,
+                                                     P.qo[out], P.qd[out], counts + k + 1, used + k, P.st_a, P.st_b, P.st_c);
             ctx->launches++;
         }
     }
     {
         Prof pr(ctx, &ctx->ms_other);
-        k_resolve<<<ctx->shade_grid, 256, 0, st>>>(p, ctx->st_c, d_accum, d_first, d_last, write_first, write_last);
+        if (wait_for) CK(cudaStreamWaitEvent(st, wait_for, 0));
+        k_resolve<<<ctx->shade_grid, 256, 0, st>>>(p, P.st_c, d_accum, d_first, d_last, write_first, write_last);
         k_stats<<<1, 32, 0, st>>>(counts, used, D, lights ? 1 : 0, ctx->d_stats);
         ctx->launches += 2;
+        CK(cudaEventRecord(P.resolved, st));
     }
     CK(cudaGetLastError());
     return 0;
@@ -309,32 +331,52 @@ int render_impl(ort_ctx* ctx, uint32_t w, uint32_t h, int32_t depth, uint64_t fi
     if (depth < 0) return fail(ctx, "ray_depth must be >= 0");
     const uint64_t npix = (uint64_t)w * h;
     if (npix > (1ull << 31)) return fail(ctx, "image too large");
-    int64_t cap = ctx->capacity_cfg > 0 ? ctx->capacity_cfg : ((int64_t)1 << 23);
+    int64_t cap = ctx->capacity_cfg > 0 ? ctx->capacity_cfg : ((int64_t)1 << 24); // paths per wave (x up to 4 overlapped waves)
     if ((uint64_t)cap < npix) cap = (int64_t)npix;
     uint64_t per_wave = std::max<uint64_t>(1, (uint64_t)cap / npix);
     if (per_wave > n_samples) per_wave = std::max<uint64_t>(n_samples, 1);
-    if (ensure_paths(ctx, (int64_t)(per_wave * npix))) return 1;
-    if (ensure_counters(ctx, depth)) return 1;
+    // two wave pipelines on two streams: the tail of every persistent kernel of one wave (a few
+    // warps finishing their last rays) is filled by the other wave's kernels
+    const uint64_t n_waves = (n_samples + per_wave - 1) / per_wave;
+    int pipes = std::max(1, std::min(ctx->overlap, MAX_PIPES));
+    if (ctx->profiling || interrupt || depth == 0) pipes = 1;
+    if ((uint64_t)pipes > n_waves) pipes = (int)n_waves;
+    if (ensure_paths(ctx, (int64_t)(per_wave * npix), pipes)) return 1;
+    if (ensure_counters(ctx, depth, pipes)) return 1;
     RenderParams p;
     fill_params(ctx, w, h, depth, &p);
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    uint64_t done = 0;
+    if (pipes > 1) {
+        CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        for (int i = 1; i < pipes; i++) CK(cudaStreamWaitEvent(ctx->aux_stream[i], ctx->ev_fork, 0));
+    }
+    uint64_t done = 0, wave = 0;
+    cudaEvent_t prev = nullptr;
     while (done < n_samples) {
         if (interrupt && *interrupt) break; // is_interrupted(), raytracer.odin:554
         const uint64_t nb = std::min<uint64_t>(per_wave, n_samples - done);
         p.sample_base = first_sample + done;
         p.n_batch_samples = (uint32_t)nb;
+        const int pi = (int)(wave % (uint64_t)pipes);
+        cudaStream_t st = pi ? ctx->aux_stream[pi] : ctx->stream;
         if (depth == 0) {
             // raytrace(depth_left = 0) returns 0 (raytracer.odin:433): count the samples, add nothing
-            CK(cudaMemsetAsync(ctx->st_c, 0, (size_t)(nb * npix) * 16, ctx->stream));
-            k_resolve<<<ctx->shade_grid, 256, 0, ctx->stream>>>(p, ctx->st_c, d_accum, d_first, d_last,
+            CK(cudaMemsetAsync(ctx->ps[0].st_c, 0, (size_t)(nb * npix) * 16, ctx->stream));
+            k_resolve<<<ctx->shade_grid, 256, 0, ctx->stream>>>(p, ctx->ps[0].st_c, d_accum, d_first, d_last,
                                                                 d_first && done == 0, d_last && done + nb == n_samples);
             ctx->launches++;
-        } else if (launch_wave(ctx, p, d_accum, d_first, d_last, d_first && done == 0, d_last != nullptr)) {
+        } else if (launch_wave(ctx, ctx->ps[pi], st, pipes > 1 ? prev : nullptr, p, d_accum, d_first, d_last,
+                               d_first && done == 0, d_last != nullptr)) {
             return 1;
         }
+        prev = ctx->ps[pi].resolved;
         done += nb;
+        wave++;
         if (interrupt) CK(cudaStreamSynchronize(ctx->stream)); // keep the poll granular: one wave
+    }
+    for (int i = 1; i < pipes; i++) {
+        CK(cudaEventRecord(ctx->ev_join[i], ctx->aux_stream[i]));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[i], 0));
     }
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     if (done_out) *done_out = done;
@@ -406,6 +448,14 @@ int ort_create(ort_ctx** out, const ort_device_cfg* cfg) {
     c->stream = c->own_stream;
     if ((e = cudaEventCreate(&c->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
     cudaEventCreate(&c->ev1); cudaEventCreate(&c->evp0); cudaEventCreate(&c->evp1);
+    cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+    for (int i = 1; i < MAX_PIPES; i++) {
+        cudaStreamCreateWithFlags(&c->aux_stream[i], cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming);
+    }
+    for (auto& P : c->ps) cudaEventCreateWithFlags(&P.resolved, cudaEventDisableTiming);
+    if (const char* e2 = std::getenv("ORT_OVERLAP")) c->overlap = std::atoi(e2);
+    if (const char* e2 = std::getenv("ORT_WAVE_PATHS")) c->capacity_cfg = std::atoll(e2);
     if ((e = cudaMalloc(&c->d_stats, 8 * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc", e);
     cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long));
     // persistent grids: as many CTAs as stay resident, a multiple of the SM count
@@ -428,7 +478,12 @@ void ort_destroy(ort_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     free_scene(ctx);
     free_paths(ctx);
-    if (ctx->counters) cudaFree(ctx->counters);
+    for (auto& P : ctx->ps) { if (P.counters) cudaFree(P.counters); if (P.resolved) cudaEventDestroy(P.resolved); }
+    cudaEventDestroy(ctx->ev_fork);
+    for (int i = 1; i < MAX_PIPES; i++) {
+        if (ctx->aux_stream[i]) { cudaStreamSynchronize(ctx->aux_stream[i]); cudaStreamDestroy(ctx->aux_stream[i]); }
+        if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
+    }
     if (ctx->d_stats) cudaFree(ctx->d_stats);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -663,10 +718,10 @@ int ort_trace_rays(ort_ctx* ctx, const ort_ray* rays, int64_t n, ort_hit* out) {
         float* d_in = ctx->scratch;
         float* d_out = ctx->scratch + (size_t)std::min<int64_t>(n, chunk) * 6;
         CK(cudaMemcpyAsync(d_in, rays + off, (size_t)m * 24, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemsetAsync(ctx->counters, 0, sizeof(uint32_t) * 8, ctx->stream));
-        k_pack_rays<<<ctx->shade_grid, 256, 0, ctx->stream>>>(d_in, m, ctx->qo[0], ctx->qd[0], ctx->counters);
-        launch_trace(ctx, ctx->qo[0], ctx->qd[0], ctx->counters, ctx->counters + 1, 0);
-        k_unpack_hits<<<ctx->shade_grid, 256, 0, ctx->stream>>>(ctx->sd, ctx->hits, ctx->qd[0], m, d_out);
+        CK(cudaMemsetAsync(ctx->ps[0].counters, 0, sizeof(uint32_t) * 8, ctx->stream));
+        k_pack_rays<<<ctx->shade_grid, 256, 0, ctx->stream>>>(d_in, m, ctx->ps[0].qo[0], ctx->ps[0].qd[0], ctx->ps[0].counters);
+        launch_trace(ctx, ctx->ps[0], ctx->stream, ctx->ps[0].qo[0], ctx->ps[0].qd[0], ctx->ps[0].counters, ctx->ps[0].counters + 1, 0);
+        k_unpack_hits<<<ctx->shade_grid, 256, 0, ctx->stream>>>(ctx->sd, ctx->ps[0].hits, ctx->ps[0].qd[0], m, d_out);
         ctx->launches += 2;
         CK(cudaMemcpyAsync(out + off, d_out, (size_t)m * 24, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
@@ -688,12 +743,12 @@ int ort_light_pdf(ort_ctx* ctx, const ort_ray* rays, int64_t n, float* out) {
     for (int64_t off = 0; off < n; off += chunk) {
         const uint32_t m = (uint32_t)std::min<int64_t>(chunk, n - off);
         CK(cudaMemcpyAsync(ctx->scratch, rays + off, (size_t)m * 24, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemsetAsync(ctx->counters, 0, sizeof(uint32_t) * 8, ctx->stream));
-        k_pack_rays<<<ctx->shade_grid, 256, 0, ctx->stream>>>(ctx->scratch, m, ctx->qo[0], ctx->qd[0], ctx->counters);
-        launch_trace(ctx, ctx->qo[0], ctx->qd[0], ctx->counters, ctx->counters + 1, 1);
-        k_scale<<<ctx->shade_grid, 256, 0, ctx->stream>>>(ctx->lsum, m, (float)ctx->sd.n_lights);
+        CK(cudaMemsetAsync(ctx->ps[0].counters, 0, sizeof(uint32_t) * 8, ctx->stream));
+        k_pack_rays<<<ctx->shade_grid, 256, 0, ctx->stream>>>(ctx->scratch, m, ctx->ps[0].qo[0], ctx->ps[0].qd[0], ctx->ps[0].counters);
+        launch_trace(ctx, ctx->ps[0], ctx->stream, ctx->ps[0].qo[0], ctx->ps[0].qd[0], ctx->ps[0].counters, ctx->ps[0].counters + 1, 1);
+        k_scale<<<ctx->shade_grid, 256, 0, ctx->stream>>>(ctx->ps[0].lsum, m, (float)ctx->sd.n_lights);
         ctx->launches += 2;
-        CK(cudaMemcpyAsync(out + off, ctx->lsum, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(out + off, ctx->ps[0].lsum, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
     CK(cudaGetLastError());
@@ -713,15 +768,15 @@ int ort_primary_hits(ort_ctx* ctx, uint32_t w, uint32_t h, uint64_t sample, ort_
     fill_params(ctx, w, h, 1, &p);
     p.sample_base = sample;
     p.n_batch_samples = 1;
-    CK(cudaMemsetAsync(ctx->counters, 0, sizeof(uint32_t) * 8, ctx->stream));
-    k_raygen<<<ctx->shade_grid, 256, 0, ctx->stream>>>(p, ctx->qo[0], ctx->qd[0], ctx->counters);
-    launch_trace(ctx, ctx->qo[0], ctx->qd[0], ctx->counters, ctx->counters + 1, 0);
-    k_unpack_hits<<<ctx->shade_grid, 256, 0, ctx->stream>>>(ctx->sd, ctx->hits, ctx->qd[0], (uint32_t)npix, ctx->scratch);
+    CK(cudaMemsetAsync(ctx->ps[0].counters, 0, sizeof(uint32_t) * 8, ctx->stream));
+    k_raygen<<<ctx->shade_grid, 256, 0, ctx->stream>>>(p, ctx->ps[0].qo[0], ctx->ps[0].qd[0], ctx->ps[0].counters);
+    launch_trace(ctx, ctx->ps[0], ctx->stream, ctx->ps[0].qo[0], ctx->ps[0].qd[0], ctx->ps[0].counters, ctx->ps[0].counters + 1, 0);
+    k_unpack_hits<<<ctx->shade_grid, 256, 0, ctx->stream>>>(ctx->sd, ctx->ps[0].hits, ctx->ps[0].qd[0], (uint32_t)npix, ctx->scratch);
     ctx->launches += 2;
     CK(cudaMemcpyAsync(out, ctx->scratch, npix * 24, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     if (rays_out) {
-        k_unpack_rays<<<ctx->shade_grid, 256, 0, ctx->stream>>>(ctx->qo[0], ctx->qd[0], (uint32_t)npix, ctx->scratch);
+        k_unpack_rays<<<ctx->shade_grid, 256, 0, ctx->stream>>>(ctx->ps[0].qo[0], ctx->ps[0].qd[0], (uint32_t)npix, ctx->scratch);
         ctx->launches++;
         CK(cudaMemcpyAsync(rays_out, ctx->scratch, npix * 24, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
