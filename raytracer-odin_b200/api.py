@@ -207,6 +207,23 @@ class MultiRenderer:
         return s.as_dict()
 
 
+def save_checkpoint(path: str, pixels: np.ndarray, next_sample: int):
+    """Raw Sample_Stats accumulators + the next sample index (the reference has no
+    checkpointing: --continious only writes on exit, main.odin:207,244)."""
+    with open(path, "wb") as f:
+        np.save(f, np.array([next_sample], np.uint64))
+        np.save(f, np.ascontiguousarray(pixels, cabi.STATS_DTYPE))
+
+
+def load_checkpoint(path: str, width: int, height: int):
+    with open(path, "rb") as f:
+        next_sample = int(np.load(f)[0])
+        pixels = np.load(f)
+    if pixels.dtype != cabi.STATS_DTYPE or pixels.size != width * height:
+        raise OrtError(f"checkpoint {path} does not match a {width}x{height} Sample_Stats image")
+    return np.ascontiguousarray(pixels), next_sample
+
+
 def mean_image(stats: np.ndarray, width: int, height: int) -> np.ndarray:
     """Linear mean radiance (total / count), image row order (row 0 = top)."""
     cnt = np.maximum(stats["count"].astype(np.float32), 1)[:, None]

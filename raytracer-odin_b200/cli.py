@@ -1,7 +1,8 @@
 """CLI mirroring the reference (main.odin:174-253):
 
     python -m raytracer_odin_b200.cli <gltf> <out.ppm|png> --width W --height H --ray-depth D \
-        --num-samples N [--env-map file.hdr] [--times T] [--continious] [--gpu G] [--seed S]
+        --num-samples N [--env-map file.hdr] [--times T] [--continious] [--gpus 0,1,..] [--seed S]
+        [--checkpoint acc.npy] [--resume acc.npy]
 
 Like the reference, render parameters default to zero when omitted (main.odin:199-206), so
 --width/--height/--ray-depth/--num-samples are effectively mandatory.  --threads is accepted and
@@ -29,8 +30,10 @@ def main(argv=None):
     ap.add_argument("--ray-depth", "-ray-depth", type=int, default=0)
     ap.add_argument("--num-samples", "-num-samples", type=int, default=0)
     ap.add_argument("--env-map", "-env-map", default="")
-    ap.add_argument("--gpu", type=int, default=0)
+    ap.add_argument("--gpus", default="0", help="comma separated CUDA device ordinals (one scene replica each)")
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--checkpoint", default="", help="write the raw Sample_Stats accumulators here on exit (.npy)")
+    ap.add_argument("--resume", default="", help="continue from accumulators written by --checkpoint")
     a = ap.parse_args(argv)
 
     scene = gltf.read_gltf(a.input_file)
@@ -45,11 +48,15 @@ def main(argv=None):
     interrupt = np.zeros(1, np.uint8)
     signal.signal(signal.SIGINT, lambda *_: interrupt.__setitem__(0, 1))  # main.odin:170-172
 
-    r = api.Renderer(device=a.gpu, seed=a.seed).upload_scene(scene)
+    devices = [int(x) for x in a.gpus.split(",")]
+    r = (api.Renderer(device=devices[0], seed=a.seed) if len(devices) == 1
+         else api.MultiRenderer(devices, seed=a.seed)).upload_scene(scene)
     w, h = a.width, a.height
-    pixels = np.zeros(w * h, cabi.STATS_DTYPE)
+    pixels, resume_at = np.zeros(w * h, cabi.STATS_DTYPE), 0
+    if a.resume:  # raw accumulators + the next sample index: the counter-based streams continue seamlessly
+        pixels, resume_at = api.load_checkpoint(a.resume, w, h)
     if a.continious:  # samples = max(int): render waves until interrupted (main.odin:207)
-        first, chunk = 0, 16
+        first, chunk = resume_at, 16
         t0 = time.perf_counter()
         while not interrupt[0]:
             r.render(w, h, a.ray_depth, chunk, first, pixels, interrupt)
@@ -60,12 +67,15 @@ def main(argv=None):
         timings = []
         for trial in range(trials):
             t0 = time.perf_counter()
-            r.render(w, h, a.ray_depth, a.num_samples, 0, pixels, interrupt)
+            r.render(w, h, a.ray_depth, a.num_samples, resume_at, pixels, interrupt)
             timings.append(time.perf_counter() - t0)
             print(f"Trial {trial} >>> Rendered in {timings[-1] * 1e3:.3f}ms")
+        first = resume_at + a.num_samples
         st = r.stats()
         total = sum(timings)
         print(f"{st['rays_closest'] / total / 1e6:.1f} Mrays/s, {st['paths'] / total / 1e6:.1f} Msamples/s")
+    if a.checkpoint:
+        api.save_checkpoint(a.checkpoint, pixels, first)
     if a.output_file:
         output.save_result(pixels, w, h, a.output_file)
     r.close()

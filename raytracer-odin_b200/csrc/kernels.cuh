@@ -296,6 +296,30 @@ __device__ f3 brdf_cos(f3 color, f3 N, float metallic, float roughness, f3 in_d,
 // sum of the ray just traced is the missing third of pdf (shading.odin:153-162), then
 // `norm_l1(value)/pdf > 1e-5` (raytracer.odin:495) decides whether this hit counts at all.
 // ------------------------------------------------------------------------------------------------
+// Can the ray reach ANY light?  Same conservative slab test as the traversal, applied to the (up
+// to four) child boxes of the light BVH's root.  Rays that fail have a light-pdf sum of exactly 0
+// (surface_sampling_pdf_bvh_sum never gets past shading.odin:86-89) and skip the light pass.
+__device__ __forceinline__ bool light_root_hit(const SceneDev& s, float4 o4, float4 d4) {
+    const RaySetup r = make_ray(o4, d4, s.pad_scale);
+    const float4* nd = s.nodes + (size_t)s.light_root * 8;
+    const float4 nxp = ldg4(nd + r.sx), fxp = ldg4(nd + (r.sx ^ 1));
+    const float4 nyp = ldg4(nd + r.sy), fyp = ldg4(nd + (r.sy ^ 1));
+    const float4 nzp = ldg4(nd + r.sz), fzp = ldg4(nd + (r.sz ^ 1));
+    const int4 ch = __ldg(reinterpret_cast<const int4*>(nd + 6));
+    bool any = false;
+#define ORT_BOX(k, C)                                                                             \
+    {                                                                                             \
+        const float tn = fmaxf(fmaxf(fmaf(nxp.k, r.ix, r.nx), fmaf(nyp.k, r.iy, r.ny)),           \
+                               fmaxf(fmaf(nzp.k, r.iz, r.nz), 0.0f));                             \
+        const float tf = fminf(fminf(fmaf(fxp.k, r.ix, r.fx), fmaf(fyp.k, r.iy, r.fy)),           \
+                               fmaf(fzp.k, r.iz, r.fz));                                          \
+        any = any || (tn <= tf && C != WIDE_EMPTY);                                               \
+    }
+    ORT_BOX(x, ch.x) ORT_BOX(y, ch.y) ORT_BOX(z, ch.z) ORT_BOX(w, ch.w)
+#undef ORT_BOX
+    return any;
+}
+
 #ifndef ORT_SHADE_MIN_CTAS
 #define ORT_SHADE_MIN_CTAS 3
 #endif
@@ -304,7 +328,8 @@ k_shade(const SceneDev s, const RenderParams p, const int bounce, const float4* 
         const float4* __restrict__ qd_in, const float4* __restrict__ hits, const float* __restrict__ lsum,
         const uint32_t* __restrict__ n_in_ptr, float4* __restrict__ qo_out, float4* __restrict__ qd_out,
         uint32_t* __restrict__ n_out_ptr, uint32_t* __restrict__ used_ptr, float4* __restrict__ st_a,
-        float4* __restrict__ st_b, float4* __restrict__ st_c) {
+        float4* __restrict__ st_b, float4* __restrict__ st_c, float* __restrict__ lsum_out,
+        uint32_t* __restrict__ lq, uint32_t* __restrict__ lq_count, const int prefilter) {
     const uint32_t n_in = *n_in_ptr;
     const int lane = threadIdx.x & 31;
     const bool has_lights = s.n_lights > 0;
@@ -454,10 +479,24 @@ k_shade(const SceneDev s, const RenderParams p, const int bounce, const float4* 
             uint32_t wbase = 0;
             if (lane == leader) wbase = atomicAdd(n_out_ptr, (uint32_t)__popc(mask));
             wbase = __shfl_sync(0xffffffffu, wbase, leader);
+            uint32_t q = 0;
             if (emit) {
-                const uint32_t q = wbase + __popc(mask & ((1u << lane) - 1u));
+                q = wbase + __popc(mask & ((1u << lane) - 1u));
                 qo_out[q] = out_o;
                 qd_out[q] = out_d;
+            }
+            if (has_lights) {
+                // second queue: only rays that can reach a light need the light-BVH pass
+                bool cand = emit;
+                if (emit && prefilter && !light_root_hit(s, out_o, out_d)) { cand = false; lsum_out[q] = 0.0f; }
+                const unsigned cmask = __ballot_sync(0xffffffffu, cand);
+                if (cmask) {
+                    const int cl = __ffs(cmask) - 1;
+                    uint32_t cbase = 0;
+                    if (lane == cl) cbase = atomicAdd(lq_count, (uint32_t)__popc(cmask));
+                    cbase = __shfl_sync(0xffffffffu, cbase, cl);
+                    if (cand) lq[cbase + __popc(cmask & ((1u << lane) - 1u))] = q;
+                }
             }
         }
     }
@@ -492,14 +531,15 @@ __global__ void k_resolve(const RenderParams p, const float4* __restrict__ st_c,
 
 // counters: [0 .. D] queue sizes per bounce; used[k]: traversals of bounce k whose result counted.
 // stats: [0] reference-equivalent closest rays  [1] light rays  [2] paths  [3] traversals launched
-__global__ void k_stats(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ used, const int depth,
-                        const int has_lights, unsigned long long* __restrict__ stats) {
+__global__ void k_stats(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ used,
+                        const uint32_t* __restrict__ lcounts, const int depth, const int has_lights,
+                        unsigned long long* __restrict__ stats) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         unsigned long long rays = 0, lrays = 0, traced = 0;
         for (int k = 0; k < depth; k++) {
             rays += used[k];
             traced += counts[k];
-            if (k > 0 && has_lights) lrays += counts[k];
+            if (k > 0 && has_lights) lrays += lcounts[k];
         }
         stats[0] += rays;
         stats[1] += lrays;

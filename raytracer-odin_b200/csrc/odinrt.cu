@@ -47,9 +47,10 @@ struct ort_ctx {
     struct PathSet {
         float4 *qo[2] = {nullptr, nullptr}, *qd[2] = {nullptr, nullptr};
         float4* hits = nullptr;
-        float* lsum = nullptr;
+        float* lsum = nullptr;  // 2 x capacity floats: ping-pong by bounce parity
+        uint32_t* lq = nullptr; // light-candidate queue (positions into the ray queue)
         float4 *st_a = nullptr, *st_b = nullptr, *st_c = nullptr;
-        uint32_t* counters = nullptr; // 4 arrays of D+2: queue counts, trace work counters, light work counters, used-ray counts
+        uint32_t* counters = nullptr; // 5 arrays of D+2: queue counts, trace / light work counters, used-ray counts, light-queue counts
         int64_t capacity = 0;
         int counters_depth = 0;
         cudaEvent_t resolved = nullptr; // recorded after this pipeline's k_resolve + k_stats
@@ -70,6 +71,7 @@ struct ort_ctx {
     int shade_grid = 0;
     bool quant = false; // scene uses QuantNode
     int fuse = 0; // env ORT_FUSE=1: trace closest hit + light sum in one fused pass
+    int light_prefilter = 1; // env ORT_LIGHT_PREFILTER=0: send every continuation ray through the light pass
     int refill = ORT_REFILL_THRESHOLD; // dynamic-fetch threshold (env ORT_REFILL, for tuning)
     int inner_min = ORT_INNER_MIN;     // inner-loop early-exit threshold (env ORT_INNER_MIN, for tuning)
     bool profiling = false;
@@ -107,10 +109,10 @@ void free_scene(ort_ctx* c) {
 }
 void free_paths(ort_ctx* c) {
     for (auto& P : c->ps) {
-        void* ptrs[] = {P.qo[0], P.qo[1], P.qd[0], P.qd[1], P.hits, P.lsum, P.st_a, P.st_b, P.st_c};
+        void* ptrs[] = {P.qo[0], P.qo[1], P.qd[0], P.qd[1], P.hits, P.lsum, P.lq, P.st_a, P.st_b, P.st_c};
         for (void* p : ptrs) if (p) cudaFree(p);
         P.qo[0] = P.qo[1] = P.qd[0] = P.qd[1] = P.hits = P.st_a = P.st_b = P.st_c = nullptr;
-        P.lsum = nullptr;
+        P.lsum = nullptr; P.lq = nullptr;
         P.capacity = 0;
     }
     c->path_bytes = 0;
@@ -184,9 +186,9 @@ int ensure_paths(ort_ctx* ctx, int64_t need, int pipes = 1) {
     for (int i = 0; i < pipes; i++) {
         auto& P = ctx->ps[i];
         if (P.capacity >= need) continue;
-        void* ptrs[] = {P.qo[0], P.qo[1], P.qd[0], P.qd[1], P.hits, P.lsum, P.st_a, P.st_b, P.st_c};
+        void* ptrs[] = {P.qo[0], P.qo[1], P.qd[0], P.qd[1], P.hits, P.lsum, P.lq, P.st_a, P.st_b, P.st_c};
         for (void* p : ptrs) if (p) cudaFree(p);
-        ctx->path_bytes -= P.capacity * (16 * 8 + 4);
+        ctx->path_bytes -= P.capacity * (16 * 8 + 12);
         P.capacity = 0;
         const size_t n = (size_t)need;
         for (int k = 0; k < 2; k++) {
@@ -194,12 +196,13 @@ int ensure_paths(ort_ctx* ctx, int64_t need, int pipes = 1) {
             CK(cudaMalloc(&P.qd[k], n * 16));
         }
         CK(cudaMalloc(&P.hits, n * 16));
-        CK(cudaMalloc(&P.lsum, n * 4));
+        CK(cudaMalloc(&P.lsum, n * 8));
+        CK(cudaMalloc(&P.lq, n * 4));
         CK(cudaMalloc(&P.st_a, n * 16));
         CK(cudaMalloc(&P.st_b, n * 16));
         CK(cudaMalloc(&P.st_c, n * 16));
         P.capacity = need;
-        ctx->path_bytes += (int64_t)(n * (16 * 8 + 4));
+        ctx->path_bytes += (int64_t)(n * (16 * 8 + 12));
     }
     return 0;
 }
@@ -209,7 +212,7 @@ int ensure_counters(ort_ctx* ctx, int depth, int pipes = 1) {
         if (P.counters && P.counters_depth >= depth) continue;
         if (P.counters) cudaFree(P.counters);
         P.counters = nullptr;
-        CK(cudaMalloc(&P.counters, sizeof(uint32_t) * 4 * (size_t)(depth + 2)));
+        CK(cudaMalloc(&P.counters, sizeof(uint32_t) * 5 * (size_t)(depth + 2)));
         P.counters_depth = depth;
     }
     return 0;
@@ -233,10 +236,11 @@ int ensure_pinned(ort_ctx* ctx, size_t bytes) {
 
 // mode 0: closest hit, 1: light-pdf sum, 2: both fused in one pass
 void launch_trace(ort_ctx* ctx, ort_ctx::PathSet& P, cudaStream_t st, const float4* qo, const float4* qd,
-                  const uint32_t* n_ptr, uint32_t* work_ctr, int mode) {
+                  const uint32_t* n_ptr, uint32_t* work_ctr, int mode, float* lsum = nullptr,
+                  const uint32_t* index = nullptr) {
     TraceArgs a;
-    a.qo = qo; a.qd = qd; a.n_ptr = n_ptr; a.work_ctr = work_ctr;
-    a.hits = P.hits; a.lsum = P.lsum;
+    a.qo = qo; a.qd = qd; a.n_ptr = n_ptr; a.work_ctr = work_ctr; a.index = index;
+    a.hits = P.hits; a.lsum = lsum ? lsum : P.lsum;
     a.refill_threshold = ctx->refill; a.inner_min = ctx->inner_min;
     const int g = ctx->trace_grid[ctx->quant ? 1 : 0][mode];
     if (!ctx->quant) {
@@ -287,28 +291,34 @@ int launch_wave(ort_ctx* ctx, ort_ctx::PathSet& P, cudaStream_t st, cudaEvent_t 
     uint32_t* wtrace = P.counters + (D + 2);
     uint32_t* wlight = P.counters + 2 * (D + 2);
     uint32_t* used = P.counters + 3 * (D + 2);
+    uint32_t* lcount = P.counters + 4 * (D + 2);
     const bool lights = ctx->sd.n_lights > 0;
+    const int prefilter = (ctx->light_prefilter && !ctx->quant) ? 1 : 0;
     {
         Prof pr(ctx, &ctx->ms_other);
-        CK(cudaMemsetAsync(P.counters, 0, sizeof(uint32_t) * 4 * (size_t)(D + 2), st));
+        CK(cudaMemsetAsync(P.counters, 0, sizeof(uint32_t) * 5 * (size_t)(D + 2), st));
         k_raygen<<<ctx->shade_grid, 256, 0, st>>>(p, P.qo[0], P.qd[0], counts);
         ctx->launches++;
     }
     for (int k = 0; k < D; k++) {
         const int in = k & 1, out = in ^ 1;
         const bool need_light = k > 0 && lights; // bounce 0 has no pending pdf to complete
+        float* lsum_in = P.lsum + (size_t)in * (size_t)P.capacity;
+        float* lsum_out = P.lsum + (size_t)out * (size_t)P.capacity;
         {
             Prof pr(ctx, &ctx->ms_trace);
-            launch_trace(ctx, P, st, P.qo[in], P.qd[in], counts + k, wtrace + k, (need_light && ctx->fuse) ? 2 : 0);
+            launch_trace(ctx, P, st, P.qo[in], P.qd[in], counts + k, wtrace + k, (need_light && ctx->fuse) ? 2 : 0, lsum_in);
         }
         if (need_light && !ctx->fuse) {
+            // only the rays k_shade queued as light candidates (the others already have lsum = 0)
             Prof pr(ctx, &ctx->ms_light);
-            launch_trace(ctx, P, st, P.qo[in], P.qd[in], counts + k, wlight + k, 1);
+            launch_trace(ctx, P, st, P.qo[in], P.qd[in], lcount + k, wlight + k, 1, lsum_in, P.lq);
         }
         {
             Prof pr(ctx, &ctx->ms_shade);
-            k_shade<<<ctx->shade_grid, 256, 0, st>>>(ctx->sd, p, k, P.qo[in], P.qd[in], P.hits, P.lsum, counts + k,
-                                                     P.qo[out], P.qd[out], counts + k + 1, used + k, P.st_a, P.st_b, P.st_c);
+            k_shade<<<ctx->shade_grid, 256, 0, st>>>(ctx->sd, p, k, P.qo[in], P.qd[in], P.hits, lsum_in, counts + k,
+                                                     P.qo[out], P.qd[out], counts + k + 1, used + k, P.st_a, P.st_b, P.st_c,
+                                                     lsum_out, P.lq, lcount + k + 1, ctx->fuse ? 0 : prefilter);
             ctx->launches++;
         }
     }
@@ -316,7 +326,7 @@ int launch_wave(ort_ctx* ctx, ort_ctx::PathSet& P, cudaStream_t st, cudaEvent_t 
         Prof pr(ctx, &ctx->ms_other);
         if (wait_for) CK(cudaStreamWaitEvent(st, wait_for, 0));
         k_resolve<<<ctx->shade_grid, 256, 0, st>>>(p, P.st_c, d_accum, d_first, d_last, write_first, write_last);
-        k_stats<<<1, 32, 0, st>>>(counts, used, D, lights ? 1 : 0, ctx->d_stats);
+        k_stats<<<1, 32, 0, st>>>(counts, used, ctx->fuse ? counts : lcount, D, lights ? 1 : 0, ctx->d_stats);
         ctx->launches += 2;
         CK(cudaEventRecord(P.resolved, st));
     }
@@ -438,6 +448,7 @@ int ort_create(ort_ctx** out, const ort_device_cfg* cfg) {
     if (const char* e2 = std::getenv("ORT_REFILL")) c->refill = std::atoi(e2);
     if (const char* e2 = std::getenv("ORT_INNER_MIN")) c->inner_min = std::atoi(e2);
     if (const char* e2 = std::getenv("ORT_FUSE")) c->fuse = std::atoi(e2);
+    if (const char* e2 = std::getenv("ORT_LIGHT_PREFILTER")) c->light_prefilter = std::atoi(e2);
     ctx = c;
     auto bail = [&](const char* what, cudaError_t err) {
         g_create_error = std::string(what) + ": " + cudaGetErrorString(err);

@@ -61,7 +61,8 @@ namespace ort {
 struct TraceArgs {
     const float4* qo;       // ray origins (xyz) + path slot (w), compacted queue order
     const float4* qd;       // ray directions
-    const uint32_t* n_ptr;  // queue size (device resident)
+    const uint32_t* index;  // optional: queue positions to process (light-candidate list); NULL = 0..n-1
+    const uint32_t* n_ptr;  // number of rays to process (device resident)
     uint32_t* work_ctr;     // persistent-thread work counter
     float4* hits;           // out: (t, u, v, tri)
     float* lsum;            // out: light pdf sum (only when do_light)
@@ -113,8 +114,9 @@ k_trace(const SceneDev s, const TraceArgs a) {
             if (lane == leader) base = atomicAdd(a.work_ctr, (uint32_t)cnt);
             base = __shfl_sync(0xffffffffu, base, leader);
             if (idle) {
-                const uint32_t idx = base + __popc(idle_mask & lt_mask);
+                uint32_t idx = base + __popc(idle_mask & lt_mask);
                 if (idx < n) {
+                    if (a.index) idx = __ldg(a.index + idx);
                     r = make_ray(ldg4(a.qo + idx), ldg4(a.qd + idx), s.pad_scale);
                     best = inf; hu = 0.0f; hv = 0.0f; htri = -1; lsumv = 0.0f; // max_dist = +inf (raytracer.odin:435)
                     cull = inf; sp = 0; pos = idx;

@@ -311,3 +311,29 @@ def test_multi_device_library_split(scenes):
         assert st["rays_closest"] == rays_one, devices
     with pytest.raises(api.OrtError):
         api.MultiRenderer([0, 99])
+
+
+def test_cli_end_to_end_and_checkpoint(scene_dir, tmp_path):
+    """The reference's command line (main.odin:174-253) through the Python mirror: PPM output,
+    --times accumulation, checkpoint + resume == one uninterrupted run."""
+    import os
+
+    from raytracer_odin_b200 import api, cli, scenegen
+
+    gltf_path = scenegen.cornell(os.path.join(scene_dir, "cli_c1.gltf"))
+    out = str(tmp_path / "a.ppm")
+    ck = str(tmp_path / "a.npy")
+    common = [gltf_path, out, "--width", "48", "--height", "32", "--ray-depth", "4", "--seed", "3"]
+    cli.main(common + ["--num-samples", "4", "--checkpoint", ck])
+    raw = open(out, "rb").read()
+    assert raw.startswith(b"P6\n48 32\n255\n") and len(raw) == len(b"P6\n48 32\n255\n") + 48 * 32 * 3
+    cli.main(common + ["--num-samples", "4", "--resume", ck, "--checkpoint", ck])
+    resumed, nxt = api.load_checkpoint(ck, 48, 32)
+    assert nxt == 8 and np.all(resumed["count"] == 8)
+    ck2 = str(tmp_path / "b.npy")
+    cli.main(common + ["--num-samples", "8", "--checkpoint", ck2])
+    full, _ = api.load_checkpoint(ck2, 48, 32)
+    np.testing.assert_allclose(resumed["total"], full["total"], rtol=1e-5, atol=1e-6)
+    cli.main(common + ["--num-samples", "2", "--times", "3", "--gpus", "0,0", "--checkpoint", ck2])
+    t3, _ = api.load_checkpoint(ck2, 48, 32)
+    assert np.all(t3["count"] == 6)
