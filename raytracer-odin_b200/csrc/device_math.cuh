@@ -61,4 +61,18 @@ __device__ __forceinline__ float u01(uint32_t r) { return (float)(r >> 8) * (1.0
 
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
 
+// 256-bit read-only global load (sm_100: LDG.E.256): one L1 wavefront per lane instead of two.
+// `p` must be 32-byte aligned.
+struct F8 {
+    float4 lo, hi;
+};
+__device__ __forceinline__ F8 ldg8(const void* p) {
+    F8 r;
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z),
+                   "=f"(r.hi.w)
+                 : "l"(p));
+    return r;
+}
+
 } // namespace ort

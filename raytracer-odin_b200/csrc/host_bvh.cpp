@@ -335,6 +335,7 @@ void make_isect_records(const ort_triangle* tris, int64_t n, TriIsect* out) {
         r.c0 = +(r.uy * r.vz - r.uz * r.vy);
         r.c1 = -(r.ux * r.vz - r.uz * r.vx);
         r.c2 = +(r.ux * r.vy - r.uy * r.vx);
+        r.pad[0] = r.pad[1] = r.pad[2] = r.pad[3] = 0.0f;
         out[i] = r;
     }
 }

@@ -43,8 +43,8 @@ struct DevTexture {
 
 struct SceneDev {
     const float4* nodes;  // WideNode[], 8 float4 each: scene BVH (root 0) followed by the light BVH
-    const float4* tris;   // TriIsect[], 3 float4 each: scene triangles followed by the light triangles
-    const float4* ltris;  // = tris + 3 * light_tri_base (light sampling, shading.odin:41-50)
+    const float4* tris;   // TriIsect[], 4 float4 (64 B) each: scene triangles followed by the light triangles
+    const float4* ltris;  // = tris + 4 * light_tri_base (light sampling, shading.odin:41-50)
     const float4* llight; // TriLight[], indexed by light triangle
     int32_t light_root;       // node index of the light BVH root inside `nodes`
     uint32_t light_tri_base;  // index of the first light triangle inside `tris`
@@ -373,7 +373,7 @@ k_shade(const SceneDev s, const RenderParams p, const int bounce, const float4* 
                     const float4 s0 = ldg4(ts), s1 = ldg4(ts + 1), s2 = ldg4(ts + 2);
                     const int4 s3 = __ldg(reinterpret_cast<const int4*>(ts + 3));
                     const DevMaterial m = s.mats[s3.x];
-                    const float4* tp = s.tris + (size_t)tri * 3;
+                    const float4* tp = s.tris + (size_t)tri * 4;
                     const float4 ta = ldg4(tp), tb = ldg4(tp + 1), tc = ldg4(tp + 2);
                     // p = trig.p + trig.u*u + trig.v*v (raytracer.odin:456), individually rounded
                     const f3 P = mk3(addr(addr(ta.x, mulr(ta.w, u)), mulr(tb.z, v)),
@@ -443,7 +443,7 @@ k_shade(const SceneDev s, const RenderParams p, const int bounce, const float4* 
                             nd = normalize3(mk3(sx * radius, sy * radius, z) + N);
                         } else if (tsel < 0.666666f && has_lights) {
                             const uint32_t idx = (uint32_t)(((uint64_t)rr.r1 * (uint64_t)(uint32_t)s.n_lights) >> 32);
-                            const float4* lp = s.ltris + (size_t)idx * 3;
+                            const float4* lp = s.ltris + (size_t)idx * 4;
                             const float4 la = ldg4(lp), lb = ldg4(lp + 1), lc = ldg4(lp + 2);
                             float su = u01(rr.r2) * (1.0f - 0.0f) + 0.0f, sv = u01(rr.r3) * (1.0f - 0.0f) + 0.0f;
                             if (su + sv > 1.0f) { su = 1.0f - su; sv = 1.0f - sv; }

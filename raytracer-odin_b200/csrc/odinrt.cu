@@ -580,8 +580,8 @@ int ort_upload_scene(ort_ctx* ctx, const ort_scene* sc) {
         make_isect_records(sc->triangles, sc->n_triangles, rec.data());
         make_isect_records(sc->light_triangles, sc->n_light_triangles, rec.data() + sc->n_triangles);
         make_light_records(sc->light_triangles, sc->n_light_triangles, lrec.data());
-        if (upload<float4>(ctx, rec.data(), rec.size() * 3, &sd.tris)) return 1;
-        sd.ltris = sd.tris + (size_t)sc->n_triangles * 3;
+        if (upload<float4>(ctx, rec.data(), rec.size() * 4, &sd.tris)) return 1;
+        sd.ltris = sd.tris + (size_t)sc->n_triangles * 4;
         if (upload<float4>(ctx, lrec.data(), lrec.size(), &sd.llight)) return 1;
         CK(cudaStreamSynchronize(ctx->stream));
     }

@@ -135,11 +135,17 @@ k_trace(const SceneDev s, const TraceArgs a) {
                     float d0, d1, d2, d3;
                     int c0, c1, c2, c3;
                     if (!QUANT) {
+                        // one 128-byte node = 3 x LDG.256 (lo|hi planes of an axis) + 1 x LDG.128 (children):
+                        // 4 L1 wavefronts per lane instead of 7; near / far picked in registers
                         const float4* nd = s.nodes + (size_t)cur * 8;
-                        const float4 nxp = ldg4(nd + r.sx), fxp = ldg4(nd + (r.sx ^ 1));
-                        const float4 nyp = ldg4(nd + r.sy), fyp = ldg4(nd + (r.sy ^ 1));
-                        const float4 nzp = ldg4(nd + r.sz), fzp = ldg4(nd + (r.sz ^ 1));
+                        const F8 px = ldg8(nd), py = ldg8(nd + 2), pz = ldg8(nd + 4);
                         const int4 ch = __ldg(reinterpret_cast<const int4*>(nd + 6));
+                        const bool ngx = r.sx & 1, ngy = r.sy & 1, ngz = r.sz & 1; // direction component negative
+#define ORT_SEL4(C, A, B) make_float4(C ? A.x : B.x, C ? A.y : B.y, C ? A.z : B.z, C ? A.w : B.w)
+                        const float4 nxp = ORT_SEL4(ngx, px.hi, px.lo), fxp = ORT_SEL4(ngx, px.lo, px.hi);
+                        const float4 nyp = ORT_SEL4(ngy, py.hi, py.lo), fyp = ORT_SEL4(ngy, py.lo, py.hi);
+                        const float4 nzp = ORT_SEL4(ngz, pz.hi, pz.lo), fzp = ORT_SEL4(ngz, pz.lo, pz.hi);
+#undef ORT_SEL4
                         c0 = ch.x; c1 = ch.y; c2 = ch.z; c3 = ch.w;
 #define ORT_BOX(k, D, C)                                                                          \
     {                                                                                             \
@@ -197,6 +203,15 @@ k_trace(const SceneDev s, const TraceArgs a) {
                         if (nh > 2) ORT_PUSH(c2, d2)
                         if (nh > 1) ORT_PUSH(c1, d1)
                         cur = c0;
+#ifdef ORT_PREFETCH
+                        // the traversal is a latency-bound dependent chain on large scenes: start pulling
+                        // the second-nearest child towards L1 while the nearest one is processed
+                        if (nh > 1) {
+                            const void* pf = c1 >= 0 ? (const void*)(s.nodes + (size_t)c1 * (QUANT ? 4 : 8))
+                                                     : (const void*)(s.tris + (size_t)(((uint32_t)~c1) >> 3) * 3);
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
+                        }
+#endif
 #ifdef ORT_SPECULATE
                         // speculative descent: park the first leaf found and keep walking inner nodes
                         if (c0 < 0 && parked == WIDE_EMPTY && sp > 0) {
@@ -221,8 +236,9 @@ k_trace(const SceneDev s, const TraceArgs a) {
                     if (CLOSEST && (!LIGHT || phase == 0)) {
                         // cast_ray_through_trigs (raytracer.odin:351-369): reference order, first wins ties
                         for (uint32_t i = 0; i < cnt; i++) {
-                            const float4* tp = s.tris + (size_t)(first + i) * 3;
-                            const float4 ta = ldg4(tp), tb = ldg4(tp + 1), tc = ldg4(tp + 2);
+                            const float4* tp = s.tris + (size_t)(first + i) * 4;
+                            const F8 tab = ldg8(tp);
+                            const float4 ta = tab.lo, tb = tab.hi, tc = ldg4(tp + 2);
                             float id, bx, by, bz, t, a00, a10;
                             tri_det_t(r, ta, tb, tc, id, bx, by, bz, t, a00, a10);
                             if (t > 0.0f && t < best) { // raytracer.odin:360
@@ -237,8 +253,9 @@ k_trace(const SceneDev s, const TraceArgs a) {
                         // surface_sampling_pdf_trigs_sum (shading.odin:52-60): the reference's intersect
                         // returns t = -1 when (u,v) is outside, then `!(t >= 0)` skips
                         for (uint32_t i = 0; i < cnt; i++) {
-                            const float4* tp = s.tris + (size_t)(first + i) * 3;
-                            const float4 ta = ldg4(tp), tb = ldg4(tp + 1), tc = ldg4(tp + 2);
+                            const float4* tp = s.tris + (size_t)(first + i) * 4;
+                            const F8 tab = ldg8(tp);
+                            const float4 ta = tab.lo, tb = tab.hi, tc = ldg4(tp + 2);
                             float id, bx, by, bz, t, a00, a10, u, v;
                             tri_det_t(r, ta, tb, tc, id, bx, by, bz, t, a00, a10);
                             if (t >= 0.0f && tri_uv(r, ta, tb, tc, id, bx, by, bz, a00, a10, u, v)) {

@@ -30,15 +30,16 @@ struct alignas(16) WideNode {
 static_assert(sizeof(WideNode) == 128, "WideNode must be one cache line");
 constexpr int32_t WIDE_EMPTY = (int32_t)0x80000000;
 
-// Traversal record, 48 bytes (3 x float4): p, u, v and the ray-independent third row of the
+// Traversal record, 64 bytes = 2 x LDG.256: p, u, v and the ray-independent third row of the
 // adjugate of [u | v | -d] (raytracer.odin:138-142): c = (uy*vz - uz*vy, -(ux*vz - uz*vx),
 // ux*vy - uy*vx), each product and difference individually rounded.
-struct alignas(16) TriIsect {
+struct alignas(32) TriIsect {
     float p[3], ux;
     float uy, uz, vx, vy;
     float vz, c0, c1, c2;
+    float pad[4];
 };
-static_assert(sizeof(TriIsect) == 48, "TriIsect");
+static_assert(sizeof(TriIsect) == 64, "TriIsect");
 
 // Extra record for light triangles (all-hit pdf sum, shading.odin:52-60): ng and
 // k = 2 / length(cross(u, v)).

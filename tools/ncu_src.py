@@ -3,6 +3,8 @@ info by instruction index): share of issued warp-instructions, average active th
 usage: ncu_src.py report.ncu-rep kernel_name launch_skip [top] [lib.so]"""
 import csv, subprocess, sys, io, os, re, tempfile, collections
 rep, kname, skip = sys.argv[1], sys.argv[2], sys.argv[3]
+# kname may be "ncu_regex:disasm_substring" (e.g. "k_trace:k_traceILb1ELb0ELb0")
+dname = kname.split(":")[1] if ":" in kname else kname
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 45
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = sys.argv[5] if len(sys.argv) > 5 else os.path.join(ROOT, "raytracer-odin_b200/csrc/libodinrt_b200.so")
@@ -24,7 +26,7 @@ dis = subprocess.run(["nvdisasm", "-g", "-c", cub], capture_output=True, text=Tr
 lines, cur, infn = [], None, False
 for l in dis.split("\n"):
     m = re.match(r"\s*\.text\.(\S+):", l)
-    if m: infn = kname in m.group(1); continue
+    if m: infn = dname in m.group(1); continue
     if not infn: continue
     m = re.search(r'//## File "([^"]+)", line (\d+)', l)
     if m: cur = (os.path.basename(m.group(1)), int(m.group(2))); continue
