@@ -321,14 +321,23 @@ def main():
         else:
             bpr = None
         trace_s = ps["trace_ms"] * 1e-3
-        n_launch = depth
+        spp_per_wave = max(1, (1 << 24) // npix)  # library default: 2^24 paths per wave
+        n_launch = depth * ((spp + spp_per_wave - 1) // spp_per_wave)  # one k_trace<closest> per bounce per wave
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", f"ncu_traffic_{args.config.lower()}.json")
+        if os.path.exists(tpath):  # dram__bytes_read+write per launch from the committed ncu --set full capture
+            with open(tpath) as f:
+                tj = json.load(f)
+            if tj.get("spp_per_wave") == spp_per_wave:
+                traffic = tj["k_trace_closest"]["dram_bytes_per_launch_avg"]
         roof = {"bound": "hbm", "kernel": "k_trace", "unit": "GB/s", "peak": peak, "peak_source": peak_src,
                 "bytes_per_ray": bpr, "n_box": counts["n_box"] if counts else None,
                 "n_tri": counts["n_tri"] if counts else None,
                 "rays_per_step": ps["rays_traced"], "launches_per_step": n_launch,
                 "kernel_ms_per_step": ps["trace_ms"], "avg_launch_ms": ps["trace_ms"] / n_launch,
                 "achieved": (bpr * ps["rays_traced"] / trace_s / 1e9) if bpr else None,
-                "traffic": None,
+                "traffic": traffic,
+                "algorithmic_bytes_per_launch": (bpr * ps["rays_traced"] / n_launch) if bpr else None,
                 "trace_grays_per_s": ps["rays_traced"] / trace_s / 1e9,
                 "step_breakdown_ms": {"trace": ps["trace_ms"], "light": ps["light_ms"], "shade": ps["shade_ms"],
                                       "other": ps["other_ms"]},

@@ -158,10 +158,13 @@ k_trace(const SceneDev s, const TraceArgs a) {
                         ORT_BOX(x, d0, c0) ORT_BOX(y, d1, c1) ORT_BOX(z, d2, c2) ORT_BOX(w, d3, c3)
 #undef ORT_BOX
                     } else {
-                        const uint4* nd = reinterpret_cast<const uint4*>(s.nodes) + (size_t)cur * 4;
-                        const uint4 v0 = __ldg(nd), v1 = __ldg(nd + 1), v2 = __ldg(nd + 2);
-                        const int4 ch = __ldg(reinterpret_cast<const int4*>(nd + 3));
-                        c0 = ch.x; c1 = ch.y; c2 = ch.z; c3 = ch.w;
+                        // 64-byte node = 2 x LDG.256
+                        const float4* nd = s.nodes + (size_t)cur * 4;
+                        const F8 q01 = ldg8(nd), q23 = ldg8(nd + 2);
+                        const uint4 v0 = make_uint4(__float_as_uint(q01.lo.x), __float_as_uint(q01.lo.y), __float_as_uint(q01.lo.z), __float_as_uint(q01.lo.w));
+                        const uint4 v1 = make_uint4(__float_as_uint(q01.hi.x), __float_as_uint(q01.hi.y), __float_as_uint(q01.hi.z), __float_as_uint(q01.hi.w));
+                        const uint4 v2 = make_uint4(__float_as_uint(q23.lo.x), __float_as_uint(q23.lo.y), 0u, 0u);
+                        c0 = __float_as_int(q23.hi.x); c1 = __float_as_int(q23.hi.y); c2 = __float_as_int(q23.hi.z); c3 = __float_as_int(q23.hi.w);
                         // plane = origin + q * step.  q is spliced into the mantissa of 1.0f (one PRMT):
                         // f = 1 + q * 2^-15, so  t = f * (2^15 step / d) + ((origin - o) / d -+ pad - 2^15 step / d)
                         const float ax_ = __uint_as_float(((v0.w & 0xffu) + 15u) << 23) * r.ix;
