@@ -337,3 +337,64 @@ def test_cli_end_to_end_and_checkpoint(scene_dir, tmp_path):
     cli.main(common + ["--num-samples", "2", "--times", "3", "--gpus", "0,0", "--checkpoint", ck2])
     t3, _ = api.load_checkpoint(ck2, 48, 32)
     assert np.all(t3["count"] == 6)
+
+
+def test_converged_4096spp_cornell(scenes, orc):
+    """BASELINE.json north_star: converged radiance within relative RMSE <= 1 % and mean luminance
+    within 0.5 % at 4096 spp (same counter-based streams on both sides)."""
+    from raytracer_odin_b200 import api
+
+    w = h = 48
+    scene = scenes("cornell", w, h)
+    with _renderer(scene) as r:
+        px = r.render(w, h, 6, 4096)
+    opx, _ = orc.OracleScene(scene).render(w, h, 6, 4096, seed=SEED, mode=1, schedule=1,
+                                           threads=orc.load().orc_hardware_threads())
+    assert np.all(px["count"] == 4096)
+    rmse, lum = api.rel_rmse(api.mean_image(px, w, h), api.mean_image(opx, w, h))
+    assert rmse <= 1e-2 and abs(lum - 1) <= 5e-3, (rmse, lum)
+    print(f"4096 spp: relRMSE {rmse:.2e}, luminance ratio {lum:.6f}")
+
+
+def _tiny_scene(n_tris, emissive=False):
+    from raytracer_odin_b200 import cabi
+    from raytracer_odin_b200.scene import Scene
+
+    s = Scene()
+    s.cam_pos = np.float32([0, 0, 3])
+    s.cam_basis = np.diag(np.float32([1, 1, -1]))
+    s.fov_x = 0.8
+    t = np.zeros(n_tris, cabi.TRI_DTYPE)
+    for i in range(n_tris):
+        t["p"][i] = [-1 + 0.1 * i, -1, -0.2 * i]
+        t["u"][i] = [2, 0, 0]
+        t["v"][i] = [0, 2, 0]
+    t["ng"] = t["n1"] = t["n2"] = t["n3"] = np.float32([0, 0, 1])
+    t["material_index"] = 1
+    s.triangles = t
+    s.materials = np.array([((0, 0, 0), -1, (0, 0, 0), -1, 0, 0, -1, -1),
+                            ((0.7, 0.6, 0.5), -1, ((2, 2, 2) if emissive else (0, 0, 0)), -1, 0.2, 0.6, -1, -1)],
+                           cabi.MAT_DTYPE)
+    return s
+
+
+@pytest.mark.parametrize("n_tris,emissive", [(0, False), (1, False), (1, True), (3, True)])
+def test_degenerate_scenes_and_odd_sizes(orc, n_tris, emissive):
+    """Ragged / minimal inputs: empty scene (one empty leaf, raytracer.odin:243-254), a single
+    triangle (root is a leaf), image sizes that are not multiples of the 4x4 tile, 1 spp, depth 1
+    and a depth far beyond the scene's needs, zero samples."""
+    from raytracer_odin_b200 import api
+
+    scene = _tiny_scene(n_tris, emissive).finish(orc.bvh_build)
+    o = orc.OracleScene(scene)
+    with _renderer(scene) as r:
+        for (w, h, depth, spp) in ((5, 3, 1, 1), (7, 9, 3, 2), (33, 2, 40, 3)):
+            g = r.primary_hits(w, h, 0)
+            ref, _, _ = o.primary_hits(w, h, sample=0, seed=SEED, mode=0)
+            _hits_equal(g, ref, f"tiny {n_tris} {w}x{h}", o.ties, max_tie_frac=1.0)
+            px = r.render(w, h, depth, spp)
+            opx, c = o.render(w, h, depth, spp, seed=SEED, mode=0)
+            assert np.array_equal(px["count"], opx["count"])
+            np.testing.assert_allclose(px["total"], opx["total"], rtol=2e-4, atol=1e-6)
+        z = r.render(4, 4, 3, 0)
+        assert np.all(z["count"] == 0)
