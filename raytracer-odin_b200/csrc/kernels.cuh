@@ -329,7 +329,8 @@ k_shade(const SceneDev s, const RenderParams p, const int bounce, const float4* 
         const uint32_t* __restrict__ n_in_ptr, float4* __restrict__ qo_out, float4* __restrict__ qd_out,
         uint32_t* __restrict__ n_out_ptr, uint32_t* __restrict__ used_ptr, float4* __restrict__ st_a,
         float4* __restrict__ st_b, float4* __restrict__ st_c, float* __restrict__ lsum_out,
-        uint32_t* __restrict__ lq, uint32_t* __restrict__ lq_count, const int prefilter) {
+        uint32_t* __restrict__ lq, uint32_t* __restrict__ lq_count, const int prefilter, const int bin_octants) {
+    __shared__ uint32_t s_cnt[16], s_off[16];
     const uint32_t n_in = *n_in_ptr;
     const int lane = threadIdx.x & 31;
     const bool has_lights = s.n_lights > 0;
@@ -472,6 +473,39 @@ k_shade(const SceneDev s, const RenderParams p, const int bounce, const float4* 
         }
         const unsigned umask = __ballot_sync(0xffffffffu, used);
         if (umask && lane == 0) atomicAdd(used_ptr, (uint32_t)__popc(umask));
+        if (bin_octants) {
+            // Queue compaction per BLOCK with an 8-bin counting sort on the direction octant: the 256
+            // paths of this iteration come from neighbouring pixels, so each run in the queue holds
+            // rays with nearby origins AND the same direction signs.  Rays fetched together by a
+            // traversal warp then share nodes (one L1 wavefront serves several lanes) and child order.
+            if (threadIdx.x < 16) s_cnt[threadIdx.x] = 0u;
+            __syncthreads();
+            const int oct = (out_d.x < 0.0f ? 1 : 0) | (out_d.y < 0.0f ? 2 : 0) | (out_d.z < 0.0f ? 4 : 0);
+            bool cand = emit && has_lights;
+            if (cand && prefilter && !light_root_hit(s, out_o, out_d)) cand = false;
+            uint32_t rank = 0, lrank = 0;
+            if (emit) rank = atomicAdd(&s_cnt[oct], 1u);
+            if (cand) lrank = atomicAdd(&s_cnt[8 + oct], 1u);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                uint32_t tot = 0, ltot = 0;
+                for (int i = 0; i < 8; i++) { tot += s_cnt[i]; ltot += s_cnt[8 + i]; }
+                uint32_t b0 = tot ? atomicAdd(n_out_ptr, tot) : 0u;
+                uint32_t b1 = ltot ? atomicAdd(lq_count, ltot) : 0u;
+                for (int i = 0; i < 8; i++) { s_off[i] = b0; b0 += s_cnt[i]; s_off[8 + i] = b1; b1 += s_cnt[8 + i]; }
+            }
+            __syncthreads();
+            if (emit) {
+                const uint32_t q = s_off[oct] + rank;
+                qo_out[q] = out_o;
+                qd_out[q] = out_d;
+                if (has_lights) {
+                    if (cand) lq[s_off[8 + oct] + lrank] = q;
+                    else lsum_out[q] = 0.0f;
+                }
+            }
+            continue;
+        }
         // queue compaction: warp ballot + prefix popcount + one atomic per warp
         const unsigned mask = __ballot_sync(0xffffffffu, emit);
         if (mask) {

@@ -71,6 +71,7 @@ struct ort_ctx {
     int shade_grid = 0;
     bool quant = false; // scene uses QuantNode
     int fuse = 0; // env ORT_FUSE=1: trace closest hit + light sum in one fused pass
+    int bin_octants = 1;     // env ORT_BIN=0: plain per-warp queue compaction (no direction-octant binning)
     int light_prefilter = 1; // env ORT_LIGHT_PREFILTER=0: send every continuation ray through the light pass
     int refill = ORT_REFILL_THRESHOLD; // dynamic-fetch threshold (env ORT_REFILL, for tuning)
     int inner_min = ORT_INNER_MIN;     // inner-loop early-exit threshold (env ORT_INNER_MIN, for tuning)
@@ -318,7 +319,7 @@ int launch_wave(ort_ctx* ctx, ort_ctx::PathSet& P, cudaStream_t st, cudaEvent_t 
             Prof pr(ctx, &ctx->ms_shade);
             k_shade<<<ctx->shade_grid, 256, 0, st>>>(ctx->sd, p, k, P.qo[in], P.qd[in], P.hits, lsum_in, counts + k,
                                                      P.qo[out], P.qd[out], counts + k + 1, used + k, P.st_a, P.st_b, P.st_c,
-                                                     lsum_out, P.lq, lcount + k + 1, ctx->fuse ? 0 : prefilter);
+                                                     lsum_out, P.lq, lcount + k + 1, ctx->fuse ? 0 : prefilter, ctx->bin_octants);
             ctx->launches++;
         }
     }
@@ -449,6 +450,7 @@ int ort_create(ort_ctx** out, const ort_device_cfg* cfg) {
     if (const char* e2 = std::getenv("ORT_INNER_MIN")) c->inner_min = std::atoi(e2);
     if (const char* e2 = std::getenv("ORT_FUSE")) c->fuse = std::atoi(e2);
     if (const char* e2 = std::getenv("ORT_LIGHT_PREFILTER")) c->light_prefilter = std::atoi(e2);
+    if (const char* e2 = std::getenv("ORT_BIN")) c->bin_octants = std::atoi(e2);
     ctx = c;
     auto bail = [&](const char* what, cudaError_t err) {
         g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
