@@ -242,6 +242,14 @@ int  ort_multi_get_stats(ort_multi* m, ort_stats* out); /* counters summed, time
  * (or a negative error code). */
 int64_t ort_bvh_build(ort_triangle* tris, int64_t n, ort_bvh_node* nodes_out, int64_t cap);
 
+/* The same builder on the GPU: identical splits, permutation and post-order
+ * node array as ort_bvh_build / the reference, every tree level processed at once (device-wide
+ * stable radix sorts on (segment, lo[axis]) keys, segmented box scans, per-segment arg-min).
+ * Host buffers in, host buffers out; returns the node count or a negative error
+ * (ort_bvh_build_device_error() holds the message). */
+int64_t ort_bvh_build_device(int32_t device, ort_triangle* tris, int64_t n, ort_bvh_node* nodes_out, int64_t cap);
+const char* ort_bvh_build_device_error(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -111,6 +111,8 @@ ABI = {
     "ort_reset_stats": (C.c_int, [C.c_void_p]),
     "ort_set_profiling": (C.c_int, [C.c_void_p, C.c_int32]),
     "ort_bvh_build": (C.c_int64, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
+    "ort_bvh_build_device": (C.c_int64, [C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
+    "ort_bvh_build_device_error": (C.c_char_p, []),
     "ort_multi_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int32, C.c_uint64]),
     "ort_multi_destroy": (None, [C.c_void_p]),
     "ort_multi_last_error": (C.c_char_p, [C.c_void_p]),

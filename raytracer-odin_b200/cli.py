@@ -15,7 +15,7 @@ import time
 import numpy as np
 
 from . import api, cabi, gltf, output
-from .scene import native_bvh_build
+from .scene import device_bvh_build, native_bvh_build
 
 
 def main(argv=None):
@@ -32,6 +32,7 @@ def main(argv=None):
     ap.add_argument("--env-map", "-env-map", default="")
     ap.add_argument("--gpus", default="0", help="comma separated CUDA device ordinals (one scene replica each)")
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--bvh", choices=("host", "device"), default="host", help="where finish_scene builds the BVHs")
     ap.add_argument("--checkpoint", default="", help="write the raw Sample_Stats accumulators here on exit (.npy)")
     ap.add_argument("--resume", default="", help="continue from accumulators written by --checkpoint")
     a = ap.parse_args(argv)
@@ -42,7 +43,7 @@ def main(argv=None):
     if a.env_map:
         scene.env_map = gltf.load_texture(a.env_map)
     t0 = time.perf_counter()
-    scene.finish(native_bvh_build)
+    scene.finish(native_bvh_build if a.bvh == "host" else device_bvh_build)
     print(f"Scene + light BVH built in {(time.perf_counter() - t0) * 1e3:.1f}ms")
 
     interrupt = np.zeros(1, np.uint8)

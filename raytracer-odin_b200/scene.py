@@ -110,3 +110,15 @@ def native_bvh_build(tris: np.ndarray) -> np.ndarray:
     if cnt < 0:
         raise RuntimeError(f"ort_bvh_build failed ({cnt})")
     return nodes[:cnt].copy()
+
+
+def device_bvh_build(tris: np.ndarray, device: int = 0) -> np.ndarray:
+    """bvh_build on the GPU (ort_bvh_build_device): same nodes and permutation as native_bvh_build."""
+    lib = cabi.load_library()
+    n = len(tris)
+    cap = max(2 * n, 1)
+    nodes = np.zeros(cap, cabi.NODE_DTYPE)
+    cnt = lib.ort_bvh_build_device(device, cabi.ptr(tris) if n else None, n, cabi.ptr(nodes), cap)
+    if cnt < 0:
+        raise RuntimeError(f"ort_bvh_build_device failed ({cnt}): {lib.ort_bvh_build_device_error().decode()}")
+    return nodes[:cnt].copy()

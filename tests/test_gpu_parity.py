@@ -398,3 +398,36 @@ def test_degenerate_scenes_and_odd_sizes(orc, n_tris, emissive):
             np.testing.assert_allclose(px["total"], opx["total"], rtol=2e-4, atol=1e-6)
         z = r.render(4, 4, 3, 0)
         assert np.all(z["count"] == 0)
+
+
+def test_device_bvh_build_equals_oracle(scene_dir, orc):
+    """ort_bvh_build_device reproduces bvh_build (raytracer.odin:227-342) exactly —
+    same post-order node array (boxes, leaf ranges, child links) and same triangle permutation as
+    the oracle's builder, on meshes, soups, heavy key ties and signed zeros."""
+    import os
+
+    from raytracer_odin_b200 import cabi, gltf, scenegen
+    from raytracer_odin_b200.scene import device_bvh_build
+    from tests.golden.make_golden import soup
+
+    def same(tris, what):
+        a, b = tris.copy(), tris.copy()
+        na, nb = orc.bvh_build(a), device_bvh_build(b)
+        assert len(na) == len(nb), what
+        assert na.tobytes() == nb.tobytes(), what
+        for f in cabi.TRI_DTYPE.names:
+            assert np.array_equal(a[f], b[f], equal_nan=True), (what, f)
+
+    same(soup(5, 1), "n=5")
+    same(soup(3000, 8), "soup 3000")
+    same(soup(70000, 9), "soup 70000")
+    g = soup(4096, 10)
+    ix = np.arange(4096)
+    g["p"] = np.stack([(ix % 16) - 8.0, ((ix // 16) % 16) - 8.0, (ix // 256) * 0.0], 1).astype(np.float32)
+    g["p"][::7, 2] = -0.0
+    g["u"], g["v"] = np.float32([1, 0, 0]), np.float32([0, 1, 0])
+    same(g, "grid with ties and signed zeros")
+    for name, kw in (("cornell", {}), ("spheres", dict(n_spheres=10, subdiv=2)), ("terrain", dict(grid=40, n_spheres=8, subdiv=1))):
+        s = gltf.read_gltf(getattr(scenegen, name)(os.path.join(scene_dir, f"db_{name}.gltf"), **kw))
+        same(s.triangles, name)
+    assert len(device_bvh_build(np.zeros(0, cabi.TRI_DTYPE))) == 1
