@@ -213,6 +213,11 @@ int  ort_light_pdf(ort_ctx* ctx, const ort_ray* rays, int64_t n, float* out);
  * accumulator to w*h*3 bytes (host). SURVEY §8(f) rank 2. */
 int  ort_tonemap_rgb8(ort_ctx* ctx, uint32_t w, uint32_t h, const float* d_accum, uint8_t* out_rgb);
 
+/* Diagnostic: time the traversal kernel alone.  Uploads n host rays once, launches the closest-hit
+ * (mode 0) or light-sum (mode 1) kernel `iters` times over them and returns the mean device time of
+ * one launch in milliseconds (CUDA events).  Used by tools/trace_bench.py to compare kernel variants. */
+int  ort_bench_trace(ort_ctx* ctx, const ort_ray* rays, int64_t n, int32_t mode, int32_t iters, double* ms_per_launch);
+
 int  ort_get_stats(ort_ctx* ctx, ort_stats* out);
 int  ort_reset_stats(ort_ctx* ctx);
 /* When on, render calls time each kernel class with CUDA events (serialises the pipeline). */

@@ -145,6 +145,13 @@ class Renderer:
                                               cabi.ptr(rays) if want_rays else None))
         return (out, rays) if want_rays else out
 
+    def bench_trace(self, rays: np.ndarray, mode: int = 0, iters: int = 10) -> float:
+        """Mean device time (ms) of one traversal-kernel launch over `rays` (diagnostic)."""
+        rays = np.ascontiguousarray(rays, cabi.RAY_DTYPE)
+        ms = C.c_double()
+        self._check(self.lib.ort_bench_trace(self._ctx, cabi.ptr(rays), len(rays), mode, iters, C.byref(ms)))
+        return ms.value
+
     # -- stats ---------------------------------------------------------------------------------
     def stats(self) -> dict:
         s = cabi.OrtStats()

@@ -743,6 +743,33 @@ int ort_trace_rays(ort_ctx* ctx, const ort_ray* rays, int64_t n, ort_hit* out) {
     return 0;
 }
 
+int ort_bench_trace(ort_ctx* ctx, const ort_ray* rays, int64_t n, int32_t mode, int32_t iters, double* ms_per_launch) {
+    if (!ctx) return 1;
+    if (!ctx->has_scene) return fail(ctx, "ort_upload_scene has not been called");
+    if (n <= 0 || n > ((int64_t)1 << 26) || !rays || !ms_per_launch || iters < 1 || mode < 0 || mode > 1)
+        return fail(ctx, "ort_bench_trace: bad arguments");
+    if (mode == 1 && ctx->sd.n_lights == 0) return fail(ctx, "ort_bench_trace: scene has no lights");
+    Bind b(ctx->device);
+    if (ensure_paths(ctx, n)) return 1;
+    if (ensure_counters(ctx, 1)) return 1;
+    if (ensure_scratch(ctx, (size_t)n * 24)) return 1;
+    auto& P = ctx->ps[0];
+    CK(cudaMemcpyAsync(ctx->scratch, rays, (size_t)n * 24, cudaMemcpyHostToDevice, ctx->stream));
+    k_pack_rays<<<ctx->shade_grid, 256, 0, ctx->stream>>>(ctx->scratch, (uint32_t)n, P.qo[0], P.qd[0], P.counters);
+    for (int it = -2; it < iters; it++) { // two warm-up launches
+        if (it == 0) CK(cudaEventRecord(ctx->evp0, ctx->stream));
+        CK(cudaMemsetAsync(P.counters + 1, 0, sizeof(uint32_t), ctx->stream));
+        launch_trace(ctx, P, ctx->stream, P.qo[0], P.qd[0], P.counters, P.counters + 1, mode);
+    }
+    CK(cudaEventRecord(ctx->evp1, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ctx->evp0, ctx->evp1));
+    *ms_per_launch = (double)ms / iters;
+    return 0;
+}
+
 int ort_light_pdf(ort_ctx* ctx, const ort_ray* rays, int64_t n, float* out) {
     if (!ctx) return 1;
     if (!ctx->has_scene) return fail(ctx, "ort_upload_scene has not been called");

@@ -37,6 +37,15 @@ namespace ort {
 #define ORT_INNER_MIN 12
 #endif
 
+// Unused child slots carry the box lo = +inf, hi = -inf (host_bvh.cpp): whatever the ray, the near
+// plane distance of the x axis is +inf and the far one -inf, so the slab test can never pass and no
+// separate validity compare is needed (ORT_CHECK_EMPTY restores it).
+#ifdef ORT_CHECK_EMPTY
+#define ORT_SLOT_OK(HIT, C) ((HIT) && (C) != WIDE_EMPTY)
+#else
+#define ORT_SLOT_OK(HIT, C) (HIT)
+#endif
+
 #define ORT_PUSH(NODE, DIST)                                                                          \
     {                                                                                                 \
         if (sp < SMEM_STACK) { sh_node[sp][threadIdx.x] = (NODE); sh_dist[sp][threadIdx.x] = (DIST); } \
@@ -96,9 +105,6 @@ k_trace(const SceneDev s, const TraceArgs a) {
     float best = inf, hu = 0.0f, hv = 0.0f, lsumv = 0.0f;
     float cull = inf;       // pop / box limit: best * best_pad in phase 0, +inf in phase 1
     int htri = -1, sp = 0, cur = WIDE_EMPTY;
-#ifdef ORT_SPECULATE
-    int parked = WIDE_EMPTY;
-#endif
     int phase = 0;          // 0: closest hit on the scene BVH, 1: all-hit sum on the light BVH
     uint32_t pos = 0;
     bool exhausted = false; // warp-uniform: the queue has no unclaimed rays left
@@ -153,7 +159,7 @@ k_trace(const SceneDev s, const TraceArgs a) {
                                fmaxf(fmaf(nzp.k, r.iz, r.nz), 0.0f));                             \
         const float tf = fminf(fminf(fmaf(fxp.k, r.ix, r.fx), fmaf(fyp.k, r.iy, r.fy)),           \
                                fminf(fmaf(fzp.k, r.iz, r.fz), cull));                             \
-        D = (tn <= tf && C != WIDE_EMPTY) ? tn : inf;                                             \
+        D = ORT_SLOT_OK(tn <= tf, C) ? tn : inf;                                                  \
     }
                         ORT_BOX(x, d0, c0) ORT_BOX(y, d1, c1) ORT_BOX(z, d2, c2) ORT_BOX(w, d3, c3)
 #undef ORT_BOX
@@ -206,33 +212,11 @@ k_trace(const SceneDev s, const TraceArgs a) {
                         if (nh > 2) ORT_PUSH(c2, d2)
                         if (nh > 1) ORT_PUSH(c1, d1)
                         cur = c0;
-#ifdef ORT_PREFETCH
-                        // the traversal is a latency-bound dependent chain on large scenes: start pulling
-                        // the second-nearest child towards L1 while the nearest one is processed
-                        if (nh > 1) {
-                            const void* pf = c1 >= 0 ? (const void*)(s.nodes + (size_t)c1 * (QUANT ? 4 : 8))
-                                                     : (const void*)(s.tris + (size_t)(((uint32_t)~c1) >> 3) * 3);
-                            asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
-                        }
-#endif
-#ifdef ORT_SPECULATE
-                        // speculative descent: park the first leaf found and keep walking inner nodes
-                        if (c0 < 0 && parked == WIDE_EMPTY && sp > 0) {
-                            parked = c0;
-                            float dd; ORT_POP(cur, dd) (void)dd;
-                        }
-#endif
                     }
                     // lanes that already hold a leaf wait at the end of this loop: once too few lanes
                     // are still descending, stop and let the waiting lanes test their triangles
                     if (__popc(__activemask()) < a.inner_min) break;
                 }
-#ifdef ORT_SPECULATE
-                if (parked != WIDE_EMPTY) { // test the parked leaf first; keep `cur` for the next round
-                    if (cur != WIDE_EMPTY) ORT_PUSH(cur, 0.0f)
-                    cur = parked; parked = WIDE_EMPTY;
-                }
-#endif
                 if (cur < 0 && cur != WIDE_EMPTY) {
                     const uint32_t code = (uint32_t)~cur;
                     const uint32_t first = code >> 3, cnt = code & 7u;
