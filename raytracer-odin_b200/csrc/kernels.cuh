@@ -190,16 +190,21 @@ __global__ void k_raygen(const RenderParams p, float4* __restrict__ qo, float4* 
 // textures (textures.odin:79-135): texel fetches through texture objects (point, unnormalised),
 // repeat wrap by floored modulo, no half-texel offset, bilinear weights in f32.
 // ------------------------------------------------------------------------------------------------
+// Odin's `%%` (floored modulo) on the integer texel coordinate (textures.odin:120-121).  32-bit
+// arithmetic: identical to the reference's i64 for |uv * dims| < 2^31 texels (the conversion
+// saturates beyond that, where f32 texel coordinates carry no sub-texel information anyway).
 __device__ __forceinline__ int wrap_i(float f, int m) {
-    long long i = (long long)f;
-    long long r = i % m;
-    return (int)(r < 0 ? r + m : r);
+    const int i = __float2int_rz(f);
+    const int r = i % m;
+    return r < 0 ? r + m : r;
 }
 __device__ __forceinline__ float lerp1(float a, float b, float t) { return a * (1.0f - t) + b * t; }
 __device__ __forceinline__ float4 lerp4(float4 a, float4 b, float t) {
     return make_float4(lerp1(a.x, b.x, t), lerp1(a.y, b.y, t), lerp1(a.z, b.z, t), lerp1(a.w, b.w, t));
 }
-__device__ __forceinline__ float4 texture_sample(const DevTexture& tx, bool srgb, float cu, float cv) {
+// Not inlined: five call sites (metallic-roughness, normal, colour, emission, environment) would
+// otherwise replicate ~180 instructions each in a kernel that already exceeds the instruction cache.
+__device__ __noinline__ float4 texture_sample(const DevTexture& tx, bool srgb, float cu, float cv) {
     const cudaTextureObject_t obj = srgb ? tx.linear : tx.raw;
     const float pcx = cu * (float)tx.w, pcy = cv * (float)tx.h;
     const float lox = floorf(pcx), loy = floorf(pcy);
