@@ -196,6 +196,8 @@ def main():
     ap.add_argument("--config", default="C2")
     ap.add_argument("--spp", type=int, default=0, help="samples per step (default: the config's spp)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--bvh", choices=("host", "device"), default="host",
+                    help="builder used by finish_scene before the timed region (identical output)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -208,7 +210,7 @@ def main():
     import torch.distributed as dist
 
     from raytracer_odin_b200 import api, multigpu
-    from raytracer_odin_b200.scene import native_bvh_build
+    from raytracer_odin_b200.scene import device_bvh_build, native_bvh_build
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -219,7 +221,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    scene, cfg = build_scene(args.config, native_bvh_build)
+    scene, cfg = build_scene(args.config, native_bvh_build if args.bvh == "host"
+                             else (lambda t: device_bvh_build(t, local)))
     w, h, depth = cfg["width"], cfg["height"], cfg["ray_depth"]
     spp = args.spp or cfg["spp"] or 64
     npix = w * h
