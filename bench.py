@@ -278,10 +278,15 @@ def main():
     out = np.zeros(npix, dtype=api.cabi.STATS_DTYPE)
     e2e_steps = max(2, min(args.steps, 3))
 
+    e2e_parts = []
+
     def e2e_step(i):
         first, cnt = multigpu.sample_partition(i * spp * world, spp * world, rank, world)
+        ta = time.perf_counter()
         r.upload_scene(scene)
+        tb = time.perf_counter()
         r.render(w, h, depth, cnt, first, out)
+        e2e_parts.append(((tb - ta) * 1e3, (time.perf_counter() - tb) * 1e3))
 
     e2e_step(0)
     r.reset_stats()
@@ -358,6 +363,8 @@ def main():
             "rays_traced_per_s": traced / (ms * 1e-3),
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(npix * 52), "steps": e2e_steps,
+                    "upload_ms": [round(a, 2) for a, _ in e2e_parts[1:]],
+                    "render_ms": [round(b, 2) for _, b in e2e_parts[1:]],
                     "what": "ort_upload_scene (host scene -> HBM, wide-BVH re-emission) + ort_render into host "
                             "Sample_Stats, wall clock"},
             "gpu_launches": int(launches), "clocks": clocks.summary(),

@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -36,9 +38,21 @@ struct ort_ctx {
     bool has_scene = false;
     SceneDev sd{};
     ort_camera cam{};
-    std::vector<void*> scene_allocs;
-    std::vector<cudaArray_t> scene_arrays;
-    std::vector<cudaTextureObject_t> scene_textures;
+    // Scene memory is pooled: buffers only ever grow and texture arrays are recycled by size, so
+    // re-uploading a scene of the same shape performs no cudaMalloc / cudaFree (a cudaFree was
+    // measured at 15-600 ms on B200 boxes: it synchronises the device and unmaps).
+    struct DevBuf { void* p = nullptr; size_t cap = 0, used = 0; };
+    enum { SB_NODES, SB_TRIS, SB_LLIGHT, SB_MATS, SB_TSHADE, SB_TUV, SB_TTAN, SB_TEXS, SB_COUNT };
+    DevBuf sbuf[SB_COUNT];
+    struct TexSlot { cudaArray_t arr = nullptr; cudaTextureObject_t obj = 0; size_t w = 0, h = 0; bool in_use = false; };
+    std::vector<TexSlot> tex_pool;
+    // pinned staging ring for host -> device uploads (records are built straight into it)
+    static constexpr int STAGE_SLOTS = 3;
+    static constexpr size_t STAGE_BYTES = (size_t)8 << 20;
+    char* stage = nullptr;
+    cudaEvent_t stage_ev[STAGE_SLOTS] = {};
+    int stage_next = 0;
+    int host_threads = 1;
     int64_t n_tris = 0, n_ltris = 0;
     WideBVH wide, lwide;
     int64_t scene_bytes = 0;
@@ -94,17 +108,37 @@ int fail(ort_ctx* c, const std::string& msg) {
             return fail(ctx, std::string(#call) + ": " + cudaGetErrorString(e_));                  \
     } while (0)
 
+// ORT_TIMING=1: wall-clock phases of the host-facing calls on stderr (diagnostic)
+struct PhaseTimer {
+    bool on;
+    const char* what;
+    std::chrono::steady_clock::time_point t;
+    std::string line;
+    explicit PhaseTimer(const char* w) : on(std::getenv("ORT_TIMING") != nullptr), what(w), t(std::chrono::steady_clock::now()) {}
+    void mark(const char* name) {
+        if (!on) return;
+        const auto n = std::chrono::steady_clock::now();
+        char buf[96];
+        std::snprintf(buf, sizeof buf, " %s=%.2fms", name, std::chrono::duration<double, std::milli>(n - t).count());
+        line += buf;
+        t = n;
+    }
+    ~PhaseTimer() { if (on) std::fprintf(stderr, "[%s]%s\n", what, line.c_str()); }
+};
+
 struct Bind {
     int prev = -1;
     explicit Bind(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
     ~Bind() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
-void free_scene(ort_ctx* c) {
-    for (auto t : c->scene_textures) cudaDestroyTextureObject(t);
-    for (auto a : c->scene_arrays) cudaFreeArray(a);
-    for (auto p : c->scene_allocs) cudaFree(p);
-    c->scene_textures.clear(); c->scene_arrays.clear(); c->scene_allocs.clear();
+void free_scene(ort_ctx* c) { // only at destroy: uploads recycle the pools
+    for (auto& t : c->tex_pool) {
+        if (t.obj) cudaDestroyTextureObject(t.obj);
+        if (t.arr) cudaFreeArray(t.arr);
+    }
+    c->tex_pool.clear();
+    for (auto& b : c->sbuf) { if (b.p) cudaFree(b.p); b = ort_ctx::DevBuf{}; }
     c->has_scene = false;
     c->scene_bytes = 0;
 }
@@ -119,17 +153,60 @@ void free_paths(ort_ctx* c) {
     c->path_bytes = 0;
 }
 
-template <typename T>
-int upload(ort_ctx* ctx, const void* host, size_t count, const T** out) {
-    *out = nullptr;
-    size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
-    void* d = nullptr;
-    CK(cudaMalloc(&d, bytes));
-    ctx->scene_allocs.push_back(d);
-    ctx->scene_bytes += (int64_t)bytes;
-    if (count) CK(cudaMemcpyAsync(d, host, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
-    else CK(cudaMemsetAsync(d, 0, bytes, ctx->stream));
-    *out = (const T*)d;
+// fn(first, count) over [0, n) on up to ctx->host_threads threads (inline when the range is small)
+template <typename F>
+void parallel_for(ort_ctx* ctx, size_t n, size_t min_per_thread, F fn) {
+    size_t nt = std::min<size_t>((size_t)std::max(ctx->host_threads, 1), n / std::max<size_t>(min_per_thread, 1));
+    if (nt <= 1) { if (n) fn((size_t)0, n); return; }
+    std::vector<std::thread> pool;
+    const size_t per = (n + nt - 1) / nt;
+    for (size_t t = 1; t < nt; t++) {
+        const size_t a = t * per, b = std::min(n, a + per);
+        if (a < b) pool.emplace_back([=] { fn(a, b - a); });
+    }
+    fn((size_t)0, std::min(n, per));
+    for (auto& th : pool) th.join();
+}
+
+// Pooled scene buffer: grows, never shrinks.
+int scene_buffer(ort_ctx* ctx, int slot, size_t bytes, void** out) {
+    auto& b = ctx->sbuf[slot];
+    bytes = std::max<size_t>(bytes, 16);
+    if (b.cap < bytes) {
+        if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+        CK(cudaMalloc(&b.p, bytes));
+        b.cap = bytes;
+    }
+    b.used = bytes;
+    *out = b.p;
+    return 0;
+}
+
+int ensure_stage(ort_ctx* ctx) {
+    if (ctx->stage) return 0;
+    CK(cudaMallocHost((void**)&ctx->stage, ort_ctx::STAGE_BYTES * ort_ctx::STAGE_SLOTS));
+    for (auto& e : ctx->stage_ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    return 0;
+}
+
+// Host -> device upload of n records of `item` bytes produced by fill(first, count, dst): the
+// records are built (on several host threads) directly into a ring of pinned chunks, and the copy
+// of one chunk runs while the next one is being built.
+template <typename F>
+int staged_upload(ort_ctx* ctx, void* d_dst, size_t n, size_t item, size_t min_per_thread, F fill) {
+    if (n == 0) return 0;
+    if (ensure_stage(ctx)) return 1;
+    const size_t per_chunk = std::max<size_t>(1, ort_ctx::STAGE_BYTES / item);
+    for (size_t off = 0; off < n; off += per_chunk) {
+        const size_t cnt = std::min(per_chunk, n - off);
+        const int slot = ctx->stage_next;
+        ctx->stage_next = (slot + 1) % ort_ctx::STAGE_SLOTS;
+        char* h = ctx->stage + (size_t)slot * ort_ctx::STAGE_BYTES;
+        CK(cudaEventSynchronize(ctx->stage_ev[slot])); // the copy that last used this chunk is done
+        parallel_for(ctx, cnt, min_per_thread, [&](size_t a, size_t c) { fill(off + a, c, h + a * item); });
+        CK(cudaMemcpyAsync((char*)d_dst + off * item, h, cnt * item, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaEventRecord(ctx->stage_ev[slot], ctx->stream));
+    }
     return 0;
 }
 
@@ -139,47 +216,68 @@ int make_texture(ort_ctx* ctx, const ort_texture& t, bool srgb, cudaTextureObjec
     if (t.data == nullptr || t.width <= 0 || t.height <= 0 || t.channels < 1 || t.channels > 4)
         return fail(ctx, "invalid texture (data/size/channels)");
     const size_t w = (size_t)t.width, h = (size_t)t.height;
-    std::vector<float> texels(w * h * 4);
+    if (w * 16 > ort_ctx::STAGE_BYTES) return fail(ctx, "texture too wide");
+    ort_ctx::TexSlot* slot = nullptr;
+    for (auto& ts : ctx->tex_pool)
+        if (!ts.in_use && ts.w == w && ts.h == h) { slot = &ts; break; }
+    if (!slot) {
+        ort_ctx::TexSlot ts;
+        ts.w = w; ts.h = h;
+        cudaChannelFormatDesc desc = cudaCreateChannelDesc<float4>();
+        CK(cudaMallocArray(&ts.arr, &desc, w, h));
+        cudaResourceDesc rd{};
+        rd.resType = cudaResourceTypeArray;
+        rd.res.array.array = ts.arr;
+        cudaTextureDesc td{};
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModePoint;
+        td.readMode = cudaReadModeElementType;
+        td.normalizedCoords = 0;
+        if (cudaError_t e = cudaCreateTextureObject(&ts.obj, &rd, &td, nullptr); e != cudaSuccess) {
+            cudaFreeArray(ts.arr);
+            return fail(ctx, std::string("cudaCreateTextureObject: ") + cudaGetErrorString(e));
+        }
+        ctx->tex_pool.push_back(ts);
+        slot = &ctx->tex_pool.back();
+    }
+    slot->in_use = true;
+    ctx->scene_bytes += (int64_t)(w * h * 16);
     float lut[256];
     for (int i = 0; i < 256; i++) {
         float x = (float)i / 255.0f;
         lut[i] = srgb ? std::pow(x, 2.2f) : x;
     }
-    for (size_t y = 0; y < h; y++)
-        for (size_t x = 0; x < w; x++) {
-            float px[4] = {1, 1, 1, 1};
-            const size_t idx = y * (size_t)t.stride + x * (size_t)t.channels;
-            for (int c = 0; c < t.channels; c++) {
-                if (t.is_f32) {
-                    float v = ((const float*)t.data)[idx + c];
-                    px[c] = (srgb && c < 3) ? std::pow(v, 2.2f) : v;
-                } else {
-                    uint8_t v = ((const uint8_t*)t.data)[idx + c];
-                    px[c] = c < 3 ? lut[v] : (float)v / 255.0f;
+    if (ensure_stage(ctx)) return 1;
+    const size_t rows_per_chunk = std::max<size_t>(1, ort_ctx::STAGE_BYTES / (w * 16));
+    for (size_t y0 = 0; y0 < h; y0 += rows_per_chunk) {
+        const size_t rows = std::min(rows_per_chunk, h - y0);
+        const int sl = ctx->stage_next;
+        ctx->stage_next = (sl + 1) % ort_ctx::STAGE_SLOTS;
+        float* texels = (float*)(ctx->stage + (size_t)sl * ort_ctx::STAGE_BYTES);
+        CK(cudaEventSynchronize(ctx->stage_ev[sl]));
+        parallel_for(ctx, rows, 16, [&](size_t ra, size_t rc) {
+            for (size_t y = y0 + ra; y < y0 + ra + rc; y++)
+                for (size_t x = 0; x < w; x++) {
+                    float px[4] = {1, 1, 1, 1};
+                    const size_t idx = y * (size_t)t.stride + x * (size_t)t.channels;
+                    for (int c = 0; c < t.channels; c++) {
+                        if (t.is_f32) {
+                            float v = ((const float*)t.data)[idx + c];
+                            px[c] = (srgb && c < 3) ? std::pow(v, 2.2f) : v;
+                        } else {
+                            uint8_t v = ((const uint8_t*)t.data)[idx + c];
+                            px[c] = c < 3 ? lut[v] : (float)v / 255.0f;
+                        }
+                    }
+                    if (srgb) // linalg.pow(pixel.rgb, 2.2) also hits the default 1.0 of absent channels: pow(1, 2.2) = 1
+                        for (int c = t.channels; c < 3; c++) px[c] = 1.0f;
+                    std::memcpy(&texels[((y - y0) * w + x) * 4], px, 16);
                 }
-            }
-            if (srgb) // linalg.pow(pixel.rgb, 2.2) also hits the default 1.0 of absent channels: pow(1, 2.2) = 1
-                for (int c = t.channels; c < 3; c++) px[c] = 1.0f;
-            std::memcpy(&texels[(y * w + x) * 4], px, 16);
-        }
-    cudaChannelFormatDesc desc = cudaCreateChannelDesc<float4>();
-    cudaArray_t arr = nullptr;
-    CK(cudaMallocArray(&arr, &desc, w, h));
-    ctx->scene_arrays.push_back(arr);
-    ctx->scene_bytes += (int64_t)(w * h * 16);
-    CK(cudaMemcpy2DToArray(arr, 0, 0, texels.data(), w * 16, w * 16, h, cudaMemcpyHostToDevice));
-    cudaResourceDesc rd{};
-    rd.resType = cudaResourceTypeArray;
-    rd.res.array.array = arr;
-    cudaTextureDesc td{};
-    td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
-    td.filterMode = cudaFilterModePoint;
-    td.readMode = cudaReadModeElementType;
-    td.normalizedCoords = 0;
-    cudaTextureObject_t obj = 0;
-    CK(cudaCreateTextureObject(&obj, &rd, &td, nullptr));
-    ctx->scene_textures.push_back(obj);
-    *out = obj;
+        });
+        CK(cudaMemcpy2DToArrayAsync(slot->arr, 0, y0, texels, w * 16, w * 16, rows, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaEventRecord(ctx->stage_ev[sl], ctx->stream));
+    }
+    *out = slot->obj;
     return 0;
 }
 
@@ -398,23 +496,27 @@ int render_impl(ort_ctx* ctx, uint32_t w, uint32_t h, int32_t depth, uint64_t fi
 // Device accumulators (+ first / last planes) -> packed Sample_Stats -> pinned host -> merged into
 // `out` like repeated rc_set_pixel calls would (main.odin:96-101).
 int pack_and_merge(ort_ctx* ctx, const float* accum, const float* first, const float* last, size_t npix,
-                   uint32_t* packed, ort_sample_stats* out) {
+                   uint32_t* packed, ort_sample_stats* out, PhaseTimer* pt = nullptr) {
     k_pack_stats<<<ctx->shade_grid, 256, 0, ctx->stream>>>(accum, first, last, (uint32_t)npix, packed);
     ctx->launches++;
     if (ensure_pinned(ctx, npix * 52)) return 1;
     CK(cudaMemcpyAsync(ctx->pinned, packed, npix * 52, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (pt) pt->mark("render+d2h");
     float ms = 0;
     if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->ms_render = ms; else cudaGetLastError();
     const ort_sample_stats* src = (const ort_sample_stats*)ctx->pinned;
-    for (size_t i = 0; i < npix; i++) {
-        if (src[i].count == 0) continue;
-        ort_sample_stats& d = out[i];
-        if (d.count == 0) std::memcpy(d.first, src[i].first, 12);
-        d.count += src[i].count;
-        std::memcpy(d.last, src[i].last, 12);
-        for (int c = 0; c < 3; c++) { d.total[c] += src[i].total[c]; d.total_squared[c] += src[i].total_squared[c]; }
-    }
+    parallel_for(ctx, npix, 1 << 16, [&](size_t f, size_t n) {
+        for (size_t i = f; i < f + n; i++) {
+            if (src[i].count == 0) continue;
+            ort_sample_stats& d = out[i];
+            if (d.count == 0) std::memcpy(d.first, src[i].first, 12);
+            d.count += src[i].count;
+            std::memcpy(d.last, src[i].last, 12);
+            for (int c = 0; c < 3; c++) { d.total[c] += src[i].total[c]; d.total_squared[c] += src[i].total_squared[c]; }
+        }
+    });
+    if (pt) pt->mark("merge");
     return 0;
 }
 
@@ -446,6 +548,8 @@ int ort_create(ort_ctx** out, const ort_device_cfg* cfg) {
     c->sm_count = prop.multiProcessorCount;
     c->seed = cfg ? cfg->seed : 0;
     c->capacity_cfg = cfg ? cfg->max_paths_in_flight : 0;
+    c->host_threads = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    if (const char* e2 = std::getenv("ORT_HOST_THREADS")) c->host_threads = std::max(1, std::atoi(e2));
     if (const char* e2 = std::getenv("ORT_REFILL")) c->refill = std::atoi(e2);
     if (const char* e2 = std::getenv("ORT_INNER_MIN")) c->inner_min = std::atoi(e2);
     if (const char* e2 = std::getenv("ORT_FUSE")) c->fuse = std::atoi(e2);
@@ -500,6 +604,8 @@ void ort_destroy(ort_ctx* ctx) {
     if (ctx->d_stats) cudaFree(ctx->d_stats);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->stage) cudaFreeHost(ctx->stage);
+    for (auto& e : ctx->stage_ev) if (e) cudaEventDestroy(e);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->evp0); cudaEventDestroy(ctx->evp1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -523,34 +629,163 @@ int ort_upload_scene(ort_ctx* ctx, const ort_scene* sc) {
     if (!ctx) return 1;
     if (!sc) return fail(ctx, "ort_upload_scene: scene is NULL");
     Bind b(ctx->device);
+    PhaseTimer pt("ort_upload_scene");
     CK(cudaStreamSynchronize(ctx->stream));
-    free_scene(ctx);
+    ctx->has_scene = false;
+    ctx->scene_bytes = 0;
+    for (auto& ts : ctx->tex_pool) ts.in_use = false;
+    for (auto& sb : ctx->sbuf) sb.used = 0;
     if (sc->n_triangles < 0 || sc->n_light_triangles < 0 || sc->n_materials < 0 || sc->n_textures < 0)
         return fail(ctx, "ort_upload_scene: negative count");
     if (sc->n_triangles >= (1 << 28)) return fail(ctx, "ort_upload_scene: more than 2^28 triangles");
-    const char* why = nullptr;
-    if (!build_wide_bvh(sc->bvh, sc->n_bvh_nodes, sc->n_triangles, &ctx->wide, &why))
-        return fail(ctx, std::string("scene BVH: ") + why);
-    if (!build_wide_bvh(sc->light_bvh, sc->n_light_bvh_nodes, sc->n_light_triangles, &ctx->lwide, &why))
-        return fail(ctx, std::string("light BVH: ") + why);
-    if (ctx->wide.max_stack > MAX_STACK || ctx->lwide.max_stack > MAX_STACK)
-        return fail(ctx, "BVH too deep for the traversal stack (worst case " + std::to_string(ctx->wide.max_stack) + " > " +
-                             std::to_string(MAX_STACK) + ")");
-    for (int64_t i = 0; i < sc->n_triangles; i++) {
-        const int64_t m = sc->triangles[i].material_index;
-        if (m < 0 || m >= sc->n_materials) return fail(ctx, "triangle material_index out of range");
-    }
+    if ((uint64_t)sc->n_triangles + (uint64_t)sc->n_light_triangles >= (1u << 28))
+        return fail(ctx, "ort_upload_scene: more than 2^28 traversal triangles");
+    if ((sc->n_triangles > 0 && !sc->triangles) || (sc->n_light_triangles > 0 && !sc->light_triangles) ||
+        (sc->n_materials > 0 && !sc->materials) || (sc->n_textures > 0 && !sc->textures))
+        return fail(ctx, "ort_upload_scene: NULL array with a non-zero count");
+    const size_t nt = (size_t)sc->n_triangles, nlt = (size_t)sc->n_light_triangles;
+
+    // The wide-BVH re-emission (serial, top-down) runs on its own host thread while this thread
+    // builds and uploads the per-triangle records, which do not depend on it.
+    const char* why_scene = nullptr;
+    const char* why_light = nullptr;
+    bool ok_scene = false, ok_light = false;
+    std::thread wide_thread([&] {
+        ok_scene = build_wide_bvh(sc->bvh, sc->n_bvh_nodes, sc->n_triangles, &ctx->wide, &why_scene);
+        ok_light = build_wide_bvh(sc->light_bvh, sc->n_light_bvh_nodes, sc->n_light_triangles, &ctx->lwide, &why_light);
+    });
+    struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{wide_thread};
+
     ctx->cam = sc->cam;
     ctx->n_tris = sc->n_triangles;
     ctx->n_ltris = sc->n_light_triangles;
     SceneDev sd{};
+    void* d = nullptr;
+
+    // materials first: they decide which optional per-triangle records are needed
+    bool any_tex = false, any_normal = false;
+    std::vector<DevMaterial> mats((size_t)sc->n_materials);
+    std::vector<char> used_raw((size_t)sc->n_textures, 0), used_lin((size_t)sc->n_textures, 0);
+    for (int64_t i = 0; i < sc->n_materials; i++) {
+        const ort_material& m = sc->materials[i];
+        DevMaterial dm{};
+        std::memcpy(dm.color, m.color_factor, 12);
+        std::memcpy(dm.emission, m.emission_factor, 12);
+        dm.roughness = m.roughness_factor;
+        dm.metallic = m.metallic_factor;
+        const int32_t ids[4] = {m.color_texture, m.emission_texture, m.metallic_roughness_texture, m.normal_texture};
+        for (int k = 0; k < 4; k++) {
+            if (ids[k] >= sc->n_textures) return fail(ctx, "material texture index out of range");
+            if (ids[k] >= 0) { any_tex = true; (k < 2 ? used_lin : used_raw)[ids[k]] = 1; }
+        }
+        if (m.normal_texture >= 0) any_normal = true;
+        dm.color_tex = ids[0] < 0 ? -1 : ids[0]; dm.emission_tex = ids[1] < 0 ? -1 : ids[1];
+        dm.mr_tex = ids[2] < 0 ? -1 : ids[2]; dm.normal_tex = ids[3] < 0 ? -1 : ids[3];
+        mats[(size_t)i] = dm;
+    }
+    if (scene_buffer(ctx, ort_ctx::SB_MATS, mats.size() * sizeof(DevMaterial), &d)) return 1;
+    sd.mats = (const DevMaterial*)d;
+    if (staged_upload(ctx, d, mats.size(), sizeof(DevMaterial), 1 << 20,
+                      [&](size_t f, size_t c, void* o) { std::memcpy(o, mats.data() + f, c * sizeof(DevMaterial)); }))
+        return 1;
+
+    // traversal records: scene triangles, then the light triangles (a ray walks both trees with the same code)
+    if (scene_buffer(ctx, ort_ctx::SB_TRIS, (nt + nlt) * sizeof(TriIsect), &d)) return 1;
+    sd.tris = (const float4*)d;
+    sd.ltris = sd.tris + nt * 4;
+    sd.light_tri_base = (uint32_t)nt;
+    if (staged_upload(ctx, d, nt, sizeof(TriIsect), 4096,
+                      [&](size_t f, size_t c, void* o) { make_isect_records(sc->triangles + f, (int64_t)c, (TriIsect*)o); }))
+        return 1;
+    if (staged_upload(ctx, (char*)d + nt * sizeof(TriIsect), nlt, sizeof(TriIsect), 4096,
+                      [&](size_t f, size_t c, void* o) { make_isect_records(sc->light_triangles + f, (int64_t)c, (TriIsect*)o); }))
+        return 1;
+    if (scene_buffer(ctx, ort_ctx::SB_LLIGHT, nlt * sizeof(TriLight), &d)) return 1;
+    sd.llight = (const float4*)d;
+    if (staged_upload(ctx, d, nlt, sizeof(TriLight), 4096,
+                      [&](size_t f, size_t c, void* o) { make_light_records(sc->light_triangles + f, (int64_t)c, (TriLight*)o); }))
+        return 1;
+    pt.mark("isect");
+
+    // shading records (+ the material_index range check of every triangle)
+    std::atomic<int> bad_material{0};
+    if (scene_buffer(ctx, ort_ctx::SB_TSHADE, nt * sizeof(TriShade), &d)) return 1;
+    sd.tshade = (const float4*)d;
+    if (staged_upload(ctx, d, nt, sizeof(TriShade), 4096, [&](size_t f, size_t c, void* o) {
+            TriShade* rec = (TriShade*)o;
+            for (size_t i = 0; i < c; i++) {
+                const ort_triangle& t = sc->triangles[f + i];
+                TriShade& r = rec[i];
+                std::memcpy(r.n1, t.n1, 12); std::memcpy(r.n2, t.n2, 12); std::memcpy(r.n3, t.n3, 12);
+                r.ngx = t.ng[0]; r.ngy = t.ng[1]; r.ngz = t.ng[2];
+                if (t.material_index < 0 || t.material_index >= sc->n_materials) bad_material.store(1, std::memory_order_relaxed);
+                r.material = (int32_t)t.material_index; r.flags = 0; r.pad0 = r.pad1 = 0;
+            }
+        }))
+        return 1;
+    if (bad_material.load()) { cudaStreamSynchronize(ctx->stream); return fail(ctx, "triangle material_index out of range"); }
+    if (any_tex) {
+        if (scene_buffer(ctx, ort_ctx::SB_TUV, nt * sizeof(TriUV), &d)) return 1;
+        sd.tuv = (const float4*)d;
+        if (staged_upload(ctx, d, nt, sizeof(TriUV), 4096, [&](size_t f, size_t c, void* o) {
+                TriUV* rec = (TriUV*)o;
+                for (size_t i = 0; i < c; i++) {
+                    const ort_triangle& t = sc->triangles[f + i];
+                    TriUV& r = rec[i];
+                    std::memcpy(r.tex1, t.tex1, 8); std::memcpy(r.tex2, t.tex2, 8); std::memcpy(r.tex3, t.tex3, 8);
+                    r.pad[0] = r.pad[1] = 0;
+                }
+            }))
+            return 1;
+    }
+    if (any_normal) {
+        if (scene_buffer(ctx, ort_ctx::SB_TTAN, nt * sizeof(TriTan), &d)) return 1;
+        sd.ttan = (const float4*)d;
+        if (staged_upload(ctx, d, nt, sizeof(TriTan), 4096, [&](size_t f, size_t c, void* o) {
+                TriTan* rec = (TriTan*)o;
+                for (size_t i = 0; i < c; i++) {
+                    const ort_triangle& t = sc->triangles[f + i];
+                    std::memcpy(rec[i].tan1, t.tan1, 16); std::memcpy(rec[i].tan2, t.tan2, 16); std::memcpy(rec[i].tan3, t.tan3, 16);
+                }
+            }))
+            return 1;
+    }
+    pt.mark("shade_records");
     {
-        // one node array (scene BVH, root 0, then the light BVH) and one traversal-triangle array
-        // (scene triangles, then the light triangles): a ray walks both trees with the same code
+        std::vector<DevTexture> texs((size_t)sc->n_textures);
+        for (int64_t i = 0; i < sc->n_textures; i++) {
+            DevTexture dt{};
+            dt.w = sc->textures[i].width; dt.h = sc->textures[i].height;
+            if (used_raw[(size_t)i] && make_texture(ctx, sc->textures[i], false, &dt.raw)) return 1;
+            if (used_lin[(size_t)i] && make_texture(ctx, sc->textures[i], true, &dt.linear)) return 1;
+            texs[(size_t)i] = dt;
+        }
+        if (scene_buffer(ctx, ort_ctx::SB_TEXS, texs.size() * sizeof(DevTexture), &d)) return 1;
+        sd.texs = (const DevTexture*)d;
+        if (staged_upload(ctx, d, texs.size(), sizeof(DevTexture), 1 << 20,
+                          [&](size_t f, size_t c, void* o) { std::memcpy(o, texs.data() + f, c * sizeof(DevTexture)); }))
+            return 1;
+    }
+    if (sc->env_map) {
+        sd.env.w = sc->env_map->width; sd.env.h = sc->env_map->height;
+        if (make_texture(ctx, *sc->env_map, false, &sd.env.raw)) return 1;
+        sd.has_env = 1;
+    }
+    pt.mark("textures");
+
+    // nodes: scene BVH (root 0) followed by the light BVH, whose references are rebased
+    wide_thread.join();
+    pt.mark("wait_wide_bvh");
+    if (!ok_scene) { cudaStreamSynchronize(ctx->stream); return fail(ctx, std::string("scene BVH: ") + why_scene); }
+    if (!ok_light) { cudaStreamSynchronize(ctx->stream); return fail(ctx, std::string("light BVH: ") + why_light); }
+    if (ctx->wide.max_stack > MAX_STACK || ctx->lwide.max_stack > MAX_STACK) {
+        cudaStreamSynchronize(ctx->stream);
+        return fail(ctx, "BVH too deep for the traversal stack (worst case " + std::to_string(ctx->wide.max_stack) + " > " +
+                             std::to_string(MAX_STACK) + ")");
+    }
+    {
         const size_t ns = ctx->wide.nodes.size(), nl = ctx->lwide.nodes.size();
-        std::vector<WideNode> nodes(ns + nl);
-        std::memcpy(nodes.data(), ctx->wide.nodes.data(), ns * sizeof(WideNode));
-        for (size_t i = 0; i < nl; i++) {
+        auto light_node = [&](size_t i) {
             WideNode w = ctx->lwide.nodes[i];
             for (int k = 0; k < 4; k++) {
                 if (w.child[k] == WIDE_EMPTY) continue;
@@ -560,107 +795,47 @@ int ort_upload_scene(ort_ctx* ctx, const ort_scene* sc) {
                     w.child[k] = ~(int32_t)((((code >> 3) + (uint32_t)sc->n_triangles) << 3) | (code & 7u));
                 }
             }
-            nodes[ns + i] = w;
-        }
-        if ((uint64_t)sc->n_triangles + (uint64_t)sc->n_light_triangles >= (1u << 28))
-            return fail(ctx, "ort_upload_scene: more than 2^28 traversal triangles");
+            return w;
+        };
         // node encoding: f32 planes by default.  The 8-bit encoding (QuantNode) halves the node
         // traffic but its decode ALU cancels the gain on every scene measured so far (C2, C4, C5:
         // profiles/r1_traversal_variants.md), so it is opt-in: ORT_QUANT=1
         ctx->quant = false;
         if (const char* e2 = std::getenv("ORT_QUANT")) ctx->quant = std::atoi(e2) != 0;
         if (ctx->quant) {
-            std::vector<QuantNode> qn(nodes.size());
-            quantize_wide_nodes(nodes.data(), nodes.size(), qn.data());
-            if (upload<float4>(ctx, qn.data(), qn.size() * 4, &sd.nodes)) return 1;
-            CK(cudaStreamSynchronize(ctx->stream));
-        } else if (upload<float4>(ctx, nodes.data(), nodes.size() * 8, &sd.nodes)) return 1;
+            std::vector<WideNode> nodes(ns + nl);
+            std::memcpy(nodes.data(), ctx->wide.nodes.data(), ns * sizeof(WideNode));
+            for (size_t i = 0; i < nl; i++) nodes[ns + i] = light_node(i);
+            if (scene_buffer(ctx, ort_ctx::SB_NODES, nodes.size() * sizeof(QuantNode), &d)) return 1;
+            if (staged_upload(ctx, d, nodes.size(), sizeof(QuantNode), 4096,
+                              [&](size_t f, size_t c, void* o) { quantize_wide_nodes(nodes.data() + f, c, (QuantNode*)o); }))
+                return 1;
+            CK(cudaStreamSynchronize(ctx->stream)); // `nodes` dies at the end of this block
+        } else {
+            if (scene_buffer(ctx, ort_ctx::SB_NODES, (ns + nl) * sizeof(WideNode), &d)) return 1;
+            if (staged_upload(ctx, d, ns, sizeof(WideNode), 8192,
+                              [&](size_t f, size_t c, void* o) { std::memcpy(o, ctx->wide.nodes.data() + f, c * sizeof(WideNode)); }))
+                return 1;
+            if (staged_upload(ctx, (char*)d + ns * sizeof(WideNode), nl, sizeof(WideNode), 8192, [&](size_t f, size_t c, void* o) {
+                    for (size_t i = 0; i < c; i++) ((WideNode*)o)[i] = light_node(f + i);
+                }))
+                return 1;
+        }
+        sd.nodes = (const float4*)d;
         sd.light_root = (int32_t)ns;
-        sd.light_tri_base = (uint32_t)sc->n_triangles;
-        std::vector<TriIsect> rec((size_t)(sc->n_triangles + sc->n_light_triangles));
-        std::vector<TriLight> lrec((size_t)sc->n_light_triangles);
-        make_isect_records(sc->triangles, sc->n_triangles, rec.data());
-        make_isect_records(sc->light_triangles, sc->n_light_triangles, rec.data() + sc->n_triangles);
-        make_light_records(sc->light_triangles, sc->n_light_triangles, lrec.data());
-        if (upload<float4>(ctx, rec.data(), rec.size() * 4, &sd.tris)) return 1;
-        sd.ltris = sd.tris + (size_t)sc->n_triangles * 4;
-        if (upload<float4>(ctx, lrec.data(), lrec.size(), &sd.llight)) return 1;
-        CK(cudaStreamSynchronize(ctx->stream));
-    }
-    bool any_tex = false, any_normal = false;
-    std::vector<DevMaterial> mats((size_t)sc->n_materials);
-    std::vector<char> used_raw((size_t)sc->n_textures, 0), used_lin((size_t)sc->n_textures, 0);
-    for (int64_t i = 0; i < sc->n_materials; i++) {
-        const ort_material& m = sc->materials[i];
-        DevMaterial d{};
-        std::memcpy(d.color, m.color_factor, 12);
-        std::memcpy(d.emission, m.emission_factor, 12);
-        d.roughness = m.roughness_factor;
-        d.metallic = m.metallic_factor;
-        const int32_t ids[4] = {m.color_texture, m.emission_texture, m.metallic_roughness_texture, m.normal_texture};
-        for (int k = 0; k < 4; k++) {
-            if (ids[k] >= sc->n_textures) return fail(ctx, "material texture index out of range");
-            if (ids[k] >= 0) { any_tex = true; (k < 2 ? used_lin : used_raw)[ids[k]] = 1; }
-        }
-        if (m.normal_texture >= 0) any_normal = true;
-        d.color_tex = ids[0] < 0 ? -1 : ids[0]; d.emission_tex = ids[1] < 0 ? -1 : ids[1];
-        d.mr_tex = ids[2] < 0 ? -1 : ids[2]; d.normal_tex = ids[3] < 0 ? -1 : ids[3];
-        mats[(size_t)i] = d;
-    }
-    if (upload<DevMaterial>(ctx, mats.data(), mats.size(), &sd.mats)) return 1;
-    {
-        std::vector<TriShade> rec((size_t)sc->n_triangles);
-        for (int64_t i = 0; i < sc->n_triangles; i++) {
-            const ort_triangle& t = sc->triangles[i];
-            TriShade& r = rec[(size_t)i];
-            std::memcpy(r.n1, t.n1, 12); std::memcpy(r.n2, t.n2, 12); std::memcpy(r.n3, t.n3, 12);
-            r.ngx = t.ng[0]; r.ngy = t.ng[1]; r.ngz = t.ng[2];
-            r.material = (int32_t)t.material_index; r.flags = 0; r.pad0 = r.pad1 = 0;
-        }
-        if (upload<float4>(ctx, rec.data(), rec.size() * 4, &sd.tshade)) return 1;
-        CK(cudaStreamSynchronize(ctx->stream));
-    }
-    if (any_tex) {
-        std::vector<TriUV> rec((size_t)sc->n_triangles);
-        for (int64_t i = 0; i < sc->n_triangles; i++) {
-            const ort_triangle& t = sc->triangles[i];
-            TriUV& r = rec[(size_t)i];
-            std::memcpy(r.tex1, t.tex1, 8); std::memcpy(r.tex2, t.tex2, 8); std::memcpy(r.tex3, t.tex3, 8);
-            r.pad[0] = r.pad[1] = 0;
-        }
-        if (upload<float4>(ctx, rec.data(), rec.size() * 2, &sd.tuv)) return 1;
-        CK(cudaStreamSynchronize(ctx->stream));
-    }
-    if (any_normal) {
-        std::vector<TriTan> rec((size_t)sc->n_triangles);
-        for (int64_t i = 0; i < sc->n_triangles; i++) {
-            const ort_triangle& t = sc->triangles[i];
-            std::memcpy(rec[(size_t)i].tan1, t.tan1, 16); std::memcpy(rec[(size_t)i].tan2, t.tan2, 16);
-            std::memcpy(rec[(size_t)i].tan3, t.tan3, 16);
-        }
-        if (upload<float4>(ctx, rec.data(), rec.size() * 3, &sd.ttan)) return 1;
-        CK(cudaStreamSynchronize(ctx->stream));
-    }
-    {
-        std::vector<DevTexture> texs((size_t)sc->n_textures);
-        for (int64_t i = 0; i < sc->n_textures; i++) {
-            DevTexture d{};
-            d.w = sc->textures[i].width; d.h = sc->textures[i].height;
-            if (used_raw[(size_t)i] && make_texture(ctx, sc->textures[i], false, &d.raw)) return 1;
-            if (used_lin[(size_t)i] && make_texture(ctx, sc->textures[i], true, &d.linear)) return 1;
-            texs[(size_t)i] = d;
-        }
-        if (upload<DevTexture>(ctx, texs.data(), texs.size(), &sd.texs)) return 1;
-        CK(cudaStreamSynchronize(ctx->stream));
-    }
-    if (sc->env_map) {
-        sd.env.w = sc->env_map->width; sd.env.h = sc->env_map->height;
-        if (make_texture(ctx, *sc->env_map, false, &sd.env.raw)) return 1;
-        sd.has_env = 1;
     }
     sd.n_lights = (int32_t)sc->n_light_triangles;
     std::memcpy(sd.pad_scale, ctx->wide.max_abs, 12);
     CK(cudaStreamSynchronize(ctx->stream));
+    pt.mark("nodes+drain");
+    // recycle what the new scene does not use (only happens when the scene's shape changed)
+    for (size_t i = 0; i < ctx->tex_pool.size();) {
+        if (ctx->tex_pool[i].in_use) { i++; continue; }
+        cudaDestroyTextureObject(ctx->tex_pool[i].obj);
+        cudaFreeArray(ctx->tex_pool[i].arr);
+        ctx->tex_pool.erase(ctx->tex_pool.begin() + (long)i);
+    }
+    for (auto& sb : ctx->sbuf) ctx->scene_bytes += (int64_t)sb.used;
     ctx->sd = sd;
     ctx->has_scene = true;
     return 0;
@@ -686,10 +861,13 @@ int ort_render(ort_ctx* ctx, uint32_t w, uint32_t h, int32_t ray_depth, uint64_t
     float* first = accum + 8 * npix;
     float* last = first + 3 * npix;
     uint32_t* packed = (uint32_t*)(last + 3 * npix);
+    PhaseTimer pt("ort_render");
     CK(cudaMemsetAsync(accum, 0, npix * 14 * 4, ctx->stream));
     uint64_t done = 0;
     if (render_impl(ctx, w, h, ray_depth, first_sample, n_samples, accum, first, last, interrupt, &done)) return 1;
-    return pack_and_merge(ctx, accum, first, last, npix, packed, out);
+    pt.mark("enqueue");
+    const int rc = pack_and_merge(ctx, accum, first, last, npix, packed, out, &pt);
+    return rc;
 }
 
 int ort_unpack_accum(ort_ctx* ctx, uint32_t w, uint32_t h, const float* d_accum, ort_sample_stats* out) {
@@ -704,7 +882,8 @@ int ort_unpack_accum(ort_ctx* ctx, uint32_t w, uint32_t h, const float* d_accum,
     CK(cudaMemcpyAsync(ctx->pinned, ctx->scratch, npix * 52, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     const ort_sample_stats* src = (const ort_sample_stats*)ctx->pinned;
-    for (size_t i = 0; i < npix; i++) {
+    parallel_for(ctx, npix, 1 << 16, [&](size_t f, size_t n) {
+    for (size_t i = f; i < f + n; i++) {
         if (src[i].count == 0) continue;
         ort_sample_stats& d = out[i];
         const float mean[3] = {src[i].total[0] / (float)src[i].count, src[i].total[1] / (float)src[i].count,
@@ -714,6 +893,7 @@ int ort_unpack_accum(ort_ctx* ctx, uint32_t w, uint32_t h, const float* d_accum,
         std::memcpy(d.last, mean, 12);
         for (int c = 0; c < 3; c++) { d.total[c] += src[i].total[c]; d.total_squared[c] += src[i].total_squared[c]; }
     }
+    });
     return 0;
 }
 
