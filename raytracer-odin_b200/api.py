@@ -214,21 +214,34 @@ class MultiRenderer:
         return s.as_dict()
 
 
-def save_checkpoint(path: str, pixels: np.ndarray, next_sample: int):
+CKPT_MAGIC = b"ORTCKPT1"
+
+
+def save_checkpoint(path: str, pixels: np.ndarray, next_sample: int, width: int = 0, height: int = 0):
     """Raw Sample_Stats accumulators + the next sample index (the reference has no
-    checkpointing: --continious only writes on exit, main.odin:207,244)."""
+    checkpointing: --continious only writes on exit, main.odin:207,244).  File format shared with the
+    C++ command line (host/main.cpp): magic | u32 width | u32 height | u64 next_sample | pixels."""
+    pixels = np.ascontiguousarray(pixels, cabi.STATS_DTYPE)
+    if width * height != pixels.size:
+        width, height = pixels.size, 1
     with open(path, "wb") as f:
-        np.save(f, np.array([next_sample], np.uint64))
-        np.save(f, np.ascontiguousarray(pixels, cabi.STATS_DTYPE))
+        f.write(CKPT_MAGIC)
+        f.write(np.array([width, height], np.uint32).tobytes())
+        f.write(np.array([next_sample], np.uint64).tobytes())
+        f.write(pixels.tobytes())
 
 
 def load_checkpoint(path: str, width: int, height: int):
     with open(path, "rb") as f:
-        next_sample = int(np.load(f)[0])
-        pixels = np.load(f)
-    if pixels.dtype != cabi.STATS_DTYPE or pixels.size != width * height:
+        raw = f.read()
+    if raw[:8] != CKPT_MAGIC or len(raw) != 24 + width * height * cabi.STATS_DTYPE.itemsize:
         raise OrtError(f"checkpoint {path} does not match a {width}x{height} Sample_Stats image")
-    return np.ascontiguousarray(pixels), next_sample
+    w, h = np.frombuffer(raw, np.uint32, 2, 8)
+    if int(w) * int(h) != width * height:
+        raise OrtError(f"checkpoint {path} does not match a {width}x{height} Sample_Stats image")
+    next_sample = int(np.frombuffer(raw, np.uint64, 1, 16)[0])
+    pixels = np.frombuffer(raw, cabi.STATS_DTYPE, width * height, 24).copy()
+    return pixels, next_sample
 
 
 def mean_image(stats: np.ndarray, width: int, height: int) -> np.ndarray:

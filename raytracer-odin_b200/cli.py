@@ -76,7 +76,7 @@ def main(argv=None):
         total = sum(timings)
         print(f"{st['rays_closest'] / total / 1e6:.1f} Mrays/s, {st['paths'] / total / 1e6:.1f} Msamples/s")
     if a.checkpoint:
-        api.save_checkpoint(a.checkpoint, pixels, first)
+        api.save_checkpoint(a.checkpoint, pixels, first, w, h)
     if a.output_file:
         output.save_result(pixels, w, h, a.output_file)
     r.close()

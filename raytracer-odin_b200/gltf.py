@@ -83,9 +83,33 @@ def _cofactor3(m: np.ndarray) -> np.ndarray:
 
 
 def _normalize_rows(v: np.ndarray) -> np.ndarray:
+    """linalg.normalize per row: v / sqrt((x*x + y*y) + z*z), every f32 operation rounded once."""
     with np.errstate(invalid="ignore", divide="ignore"):
-        ln = np.sqrt((v * v).sum(axis=1, dtype=f32)).astype(f32)
+        v = v.astype(f32)
+        ln = np.sqrt((v[:, 0] * v[:, 0] + v[:, 1] * v[:, 1]) + v[:, 2] * v[:, 2]).astype(f32)
         return (v / ln[:, None]).astype(f32)
+
+
+def _mat4_mul(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """4x4 f32 product, entries summed left to right with no fused multiply-add (numpy's matmul may
+    call a BLAS kernel with a different summation order; the C++ host uses exactly this order)."""
+    o = np.zeros((4, 4), f32)
+    for r in range(4):
+        for c in range(4):
+            o[r, c] = ((a[r, 0] * b[0, c] + a[r, 1] * b[1, c]) + a[r, 2] * b[2, c]) + a[r, 3] * b[3, c]
+    return o
+
+
+def _transform_rows(m3: np.ndarray, tr: np.ndarray, v: np.ndarray, w: float) -> np.ndarray:
+    """(transform * {v, w}).xyz for every row of v: ((m0*x + m1*y) + m2*z) + t*w, elementwise f32."""
+    v = v.astype(f32)
+    x, y, z = v[:, 0], v[:, 1], v[:, 2]
+    out = np.empty((len(v), 3), f32)
+    for r in range(3):
+        out[:, r] = (m3[r, 0] * x + m3[r, 1] * y) + m3[r, 2] * z
+        if tr is not None:
+            out[:, r] = out[:, r] + tr[r] * f32(w)
+    return out
 
 
 class _Gltf:
@@ -153,7 +177,7 @@ def read_gltf(gltf_path: str) -> Scene:
 
     def populate(node_idx: int, parent: np.ndarray):  # populate_scene input.odin:92-233
         node = j["nodes"][node_idx]
-        transform = (parent @ _node_transform_local(node)).astype(f32)
+        transform = _mat4_mul(parent, _node_transform_local(node))
         if "camera" in node:  # :103-109
             scene.cam_pos = transform[:3, 3].copy()
             basis = np.zeros((3, 3), f32)
@@ -194,7 +218,7 @@ def read_gltf(gltf_path: str) -> Scene:
 
                 m3 = transform[:3, :3]
                 tr = transform[:3, 3]
-                wp = (pos[:, :3].astype(f32) @ m3.T + tr).astype(f32)  # transform * (p,1)
+                wp = _transform_rows(m3, tr, pos[:, :3], 1.0)  # transform * (p,1)
                 P = wp[idx]  # nt x 3 x 3
                 e1 = (P[:, 1] - P[:, 0]).astype(f32)
                 e2 = (P[:, 2] - P[:, 0]).astype(f32)
@@ -204,7 +228,7 @@ def read_gltf(gltf_path: str) -> Scene:
                 T["p"], T["u"], T["v"], T["ng"] = P[:, 0], e1, e2, ng
                 if "NORMAL" in attrs:
                     cof = _cofactor3(m3)
-                    wn = _normalize_rows((g.accessor_float(attrs["NORMAL"])[:, :3].astype(f32) @ cof.T).astype(f32))
+                    wn = _normalize_rows(_transform_rows(cof, None, g.accessor_float(attrs["NORMAL"])[:, :3], 0.0))
                     N = wn[idx]
                     T["n1"], T["n2"], T["n3"] = N[:, 0], N[:, 1], N[:, 2]
                 else:
@@ -214,7 +238,7 @@ def read_gltf(gltf_path: str) -> Scene:
                     T["tex1"], T["tex2"], T["tex3"] = uv[:, 0], uv[:, 1], uv[:, 2]
                 if "TANGENT" in attrs:
                     tg = g.accessor_float(attrs["TANGENT"]).astype(f32)
-                    wt = _normalize_rows((tg[:, :3] @ m3.T).astype(f32))
+                    wt = _normalize_rows(_transform_rows(m3, tr, tg[:, :3], 0.0))
                     tg4 = np.concatenate([wt, tg[:, 3:4]], axis=1)[idx]
                 else:
                     # the reference normalises a zero tangent -> NaN xyz, w = 0 (:193-195)
