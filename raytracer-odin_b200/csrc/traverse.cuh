@@ -46,17 +46,19 @@ namespace ort {
 #define ORT_SLOT_OK(HIT, C) (HIT)
 #endif
 
+// Stack entry = (node reference, entry distance bits): one 64-bit access per push / pop.
 #define ORT_PUSH(NODE, DIST)                                                                          \
     {                                                                                                 \
-        if (sp < SMEM_STACK) { sh_node[sp][threadIdx.x] = (NODE); sh_dist[sp][threadIdx.x] = (DIST); } \
-        else { l_node[sp - SMEM_STACK] = (NODE); l_dist[sp - SMEM_STACK] = (DIST); }                  \
+        const uint2 e_ = make_uint2((uint32_t)(NODE), __float_as_uint(DIST));                         \
+        if (sp < SMEM_STACK) sh_stack[sp][threadIdx.x] = e_;                                          \
+        else l_stack[sp - SMEM_STACK] = e_;                                                           \
         sp++;                                                                                         \
     }
 #define ORT_POP(NODE, DIST)                                                                           \
     {                                                                                                 \
         sp--;                                                                                         \
-        if (sp < SMEM_STACK) { NODE = sh_node[sp][threadIdx.x]; DIST = sh_dist[sp][threadIdx.x]; }    \
-        else { NODE = l_node[sp - SMEM_STACK]; DIST = l_dist[sp - SMEM_STACK]; }                      \
+        const uint2 e_ = sp < SMEM_STACK ? sh_stack[sp][threadIdx.x] : l_stack[sp - SMEM_STACK];      \
+        NODE = (int)e_.x; DIST = __uint_as_float(e_.y);                                               \
     }
 #define ORT_CSWAP(da, ca, db, cb)               \
     {                                           \
@@ -90,10 +92,8 @@ struct TraceArgs {
 template <bool CLOSEST, bool LIGHT, bool QUANT>
 __global__ void __launch_bounds__(TRACE_THREADS, ORT_TRACE_MIN_CTAS)
 k_trace(const SceneDev s, const TraceArgs a) {
-    __shared__ int sh_node[SMEM_STACK][TRACE_THREADS];
-    __shared__ float sh_dist[SMEM_STACK][TRACE_THREADS];
-    int l_node[LOCAL_STACK];
-    float l_dist[LOCAL_STACK];
+    __shared__ uint2 sh_stack[SMEM_STACK][TRACE_THREADS];
+    uint2 l_stack[LOCAL_STACK];
 
     const uint32_t n = *a.n_ptr;
     const int lane = threadIdx.x & 31;
@@ -145,7 +145,23 @@ k_trace(const SceneDev s, const TraceArgs a) {
                         // 4 L1 wavefronts per lane instead of 7; near / far picked in registers
                         const float4* nd = s.nodes + (size_t)cur * 8;
                         const F8 px = ldg8(nd), py = ldg8(nd + 2), pz = ldg8(nd + 4);
-                        const int4 ch = __ldg(reinterpret_cast<const int4*>(nd + 6));
+                        int4 ch = __ldg(reinterpret_cast<const int4*>(nd + 6));
+#ifdef ORT_EXP_DUPLOAD
+                        // sensitivity experiment: the same 128-byte node read a second time (L1 hits, but the
+                        // wavefronts go through the LSU data pipe again); results folded in so nothing is elided
+                        {
+                            float x0, x1, x2, x3, x4, x5, x6, x7;
+                            unsigned acc = 0;
+#pragma unroll
+                            for (int kk = 0; kk < ORT_EXP_DUPLOAD; kk++) {
+                                asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                             : "=f"(x0), "=f"(x1), "=f"(x2), "=f"(x3), "=f"(x4), "=f"(x5), "=f"(x6), "=f"(x7)
+                                             : "l"(nd + 2 * (kk & 3)));
+                                acc |= __float_as_uint(x0) & __float_as_uint(x7) & 0x80000000u & (unsigned)cur;
+                            }
+                            ch.x |= (int)(acc & (acc >> 1) & 1u); // always 0 (bit 0 of a value with only bit 31 set)
+                        }
+#endif
                         const bool ngx = r.sx & 1, ngy = r.sy & 1, ngz = r.sz & 1; // direction component negative
 #define ORT_SEL4(C, A, B) make_float4(C ? A.x : B.x, C ? A.y : B.y, C ? A.z : B.z, C ? A.w : B.w)
                         const float4 nxp = ORT_SEL4(ngx, px.hi, px.lo), fxp = ORT_SEL4(ngx, px.lo, px.hi);
@@ -162,6 +178,27 @@ k_trace(const SceneDev s, const TraceArgs a) {
         D = ORT_SLOT_OK(tn <= tf, C) ? tn : inf;                                                  \
     }
                         ORT_BOX(x, d0, c0) ORT_BOX(y, d1, c1) ORT_BOX(z, d2, c2) ORT_BOX(w, d3, c3)
+#ifdef ORT_EXP_DUPALU
+                        // sensitivity experiment: ORT_EXP_DUPALU extra dependent FMAs per visit on the critical path
+                        {
+#ifdef ORT_EXP_INDEP
+                            float z0 = d0, z1 = d1, z2 = d2, z3 = d3; // four independent chains: issue slots, little latency
+#pragma unroll
+                            for (int kk = 0; kk < ORT_EXP_DUPALU / 4; kk++) {
+                                asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(z0) : "f"(r.ix), "f"(r.nx));
+                                asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(z1) : "f"(r.ix), "f"(r.nx));
+                                asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(z2) : "f"(r.ix), "f"(r.nx));
+                                asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(z3) : "f"(r.ix), "f"(r.nx));
+                            }
+                            const float z = z0 + z1 + z2 + z3;
+#else
+                            float z = d0;
+#pragma unroll
+                            for (int kk = 0; kk < ORT_EXP_DUPALU; kk++) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(z) : "f"(r.ix), "f"(r.nx));
+#endif
+                            if (z == 123.456f) d1 = z;
+                        }
+#endif
 #undef ORT_BOX
                     } else {
                         // 64-byte node = 2 x LDG.256
@@ -208,6 +245,8 @@ k_trace(const SceneDev s, const TraceArgs a) {
                             if (dd <= cull) { cur = nd2; break; }
                         }
                     } else {
+                        // (three predicated stores at precomputed slots instead of three branches measured
+                        // the same: profiles/r1_traversal_variants.md)
                         if (nh > 3) ORT_PUSH(c3, d3)
                         if (nh > 2) ORT_PUSH(c2, d2)
                         if (nh > 1) ORT_PUSH(c1, d1)

@@ -13,7 +13,12 @@ out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-n
 rows = list(csv.reader(io.StringIO(out)))
 hi = next(i for i, r in enumerate(rows) if "Source" in r and "Instructions Executed" in r)
 hdr, data = rows[hi], [r for r in rows[hi + 1:] if len(r) == len(rows[hi])]
-data = data[::2] if len(data) > 1 and data[0] == data[1] else data  # ncu prints every SASS row twice
+seen, uniq = set(), []  # ncu may print the SASS table more than once: keep the first row of every address
+for r in data:
+    if r[0] in seen or not r[0].startswith("0x"):
+        continue
+    seen.add(r[0]); uniq.append(r)
+data = uniq
 ix = {h: i for i, h in enumerate(hdr)}
 def f(r, k):
     try: return float(r[ix[k]])
@@ -21,7 +26,8 @@ def f(r, k):
 # line info
 d = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", lib], cwd=d, capture_output=True)
-cub = max((os.path.join(d, x) for x in os.listdir(d) if x.endswith(".cubin")), key=os.path.getsize)
+cubs = [os.path.join(d, x) for x in os.listdir(d) if x.endswith(".cubin")]
+cub = next((c for c in cubs if os.path.basename(c).startswith("odinrt")), max(cubs, key=os.path.getsize))
 dis = subprocess.run(["nvdisasm", "-g", "-c", cub], capture_output=True, text=True).stdout
 lines, cur, infn = [], None, False
 for l in dis.split("\n"):
