@@ -295,11 +295,18 @@ __device__ f3 brdf_cos(f3 color, f3 N, float metallic, float roughness, f3 in_d,
 
 // ------------------------------------------------------------------------------------------------
 // k_shade: one wavefront step of raytrace (raytracer.odin:432-500) in iterative form.
-// Path state by slot:  st_a = (T.rgb, cosine pdf)   st_b = (value.rgb, vndf pdf term)
-//                      st_c = (L.rgb, -)            with L = sum_k T_k * emission_k.
+// Path state: L = sum_k T_k * emission_k lives in st_c BY SLOT and is only touched when a hit adds
+// something (emissive surface, environment); the pending (T, value, pdf terms) of the sampled
+// direction travel WITH THE RAY in queue order:  pa = (T.rgb, cosine pdf)  pb = (value.rgb, vndf pdf term).
 // For bounce > 0 the pending (value, pdf) of the previous hit is completed first: the light-BVH
 // sum of the ray just traced is the missing third of pdf (shading.odin:153-162), then
 // `norm_l1(value)/pdf > 1e-5` (raytracer.odin:495) decides whether this hit counts at all.
+//
+// Two phases per block of 256 queue entries.  Phase A (one thread per entry): completes the pdf,
+// handles misses (environment lookup) and dead paths.  The entries that need the expensive part
+// (material fetch, sampling, BRDF) are then compacted inside the block, so phase B runs on dense
+// warps: 30-40 % of the rays of an open scene miss, and their lanes would otherwise idle through
+// ~600 instructions.
 // ------------------------------------------------------------------------------------------------
 // Can the ray reach ANY light?  Same conservative slab test as the traversal, applied to the (up
 // to four) child boxes of the light BVH's root.  Rays that fail have a light-pdf sum of exactly 0
@@ -328,166 +335,220 @@ __device__ __forceinline__ bool light_root_hit(const SceneDev& s, float4 o4, flo
 #ifndef ORT_SHADE_MIN_CTAS
 #define ORT_SHADE_MIN_CTAS 3
 #endif
+struct ShadeArgs {
+    const float4 *qo_in, *qd_in, *hits, *pa_in, *pb_in;
+    const float* lsum;
+    const uint32_t* n_in_ptr;
+    float4 *qo_out, *qd_out, *pa_out, *pb_out;
+    uint32_t *n_out_ptr, *used_ptr;
+    float4* st_c;
+    float* lsum_out;
+    uint32_t *lq, *lq_count;
+    int bounce, prefilter, bin_octants;
+};
+
 __global__ void __launch_bounds__(256, ORT_SHADE_MIN_CTAS)
-k_shade(const SceneDev s, const RenderParams p, const int bounce, const float4* __restrict__ qo_in,
-        const float4* __restrict__ qd_in, const float4* __restrict__ hits, const float* __restrict__ lsum,
-        const uint32_t* __restrict__ n_in_ptr, float4* __restrict__ qo_out, float4* __restrict__ qd_out,
-        uint32_t* __restrict__ n_out_ptr, uint32_t* __restrict__ used_ptr, float4* __restrict__ st_a,
-        float4* __restrict__ st_b, float4* __restrict__ st_c, float* __restrict__ lsum_out,
-        uint32_t* __restrict__ lq, uint32_t* __restrict__ lq_count, const int prefilter, const int bin_octants) {
-    __shared__ uint32_t s_cnt[16], s_off[16];
-    const uint32_t n_in = *n_in_ptr;
-    const int lane = threadIdx.x & 31;
+k_shade(const SceneDev s, const RenderParams p, const ShadeArgs a) {
+    __shared__ uint32_t s_cnt[16], s_off[16], s_wsum[8], s_qn;
+    __shared__ float4 s_q[512]; // pending work items of this block: (T.rgb, queue position)
+    const int bounce = a.bounce;
+    const uint32_t n_in = *a.n_in_ptr;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const bool has_lights = s.n_lights > 0;
-    for (uint32_t base = blockIdx.x * blockDim.x; base < n_in; base += gridDim.x * blockDim.x) {
+    if (threadIdx.x == 0) s_qn = 0u;
+    __syncthreads();
+    for (uint32_t base = blockIdx.x * blockDim.x;; base += gridDim.x * blockDim.x) {
+        // ---- phase A: complete the pending pdf, misses, dead paths
+        const bool more = base < n_in; // block-uniform: queue entries left for this block
         const uint32_t pos = base + threadIdx.x;
-        bool emit = false, used = false;
-        float4 out_o = make_float4(0, 0, 0, 0), out_d = make_float4(0, 0, 0, 0);
-        if (pos < n_in) {
-            const float4 o4 = qo_in[pos];
-            const float4 d4 = qd_in[pos];
-            const float4 h4 = hits[pos];
-            const uint32_t slot = __float_as_uint(o4.w);
-            const f3 in_d = mk3(d4.x, d4.y, d4.z);
-            f3 T = mk3(1, 1, 1), L = mk3(0, 0, 0);
+        bool used = false, heavy = false;
+        f3 T = mk3(1, 1, 1);
+        if (more && pos < n_in) {
+            const float4 h4 = a.hits[pos];
             bool alive = true;
             if (bounce > 0) {
-                const float4 a = st_a[slot], b = st_b[slot], c = st_c[slot];
-                const f3 value = mk3(b.x, b.y, b.z);
-                L = mk3(c.x, c.y, c.z);
+                const float4 pa = a.pa_in[pos], pb = a.pb_in[pos];
+                const f3 value = mk3(pb.x, pb.y, pb.z);
                 // pdf (shading.odin:158-161): (cosine + light + vndf * (1 | 2)) / 3
-                const float lp = has_lights ? lsum[pos] / (float)s.n_lights : 0.0f;
-                const float pdf = (a.w + lp + b.w) / 3.0f;
-                if (norm_l1(value) / pdf > 1e-5f) T = mk3(a.x, a.y, a.z) * value / pdf;
+                const float lp = has_lights ? a.lsum[pos] / (float)s.n_lights : 0.0f;
+                const float pdf = (pa.w + lp + pb.w) / 3.0f;
+                if (norm_l1(value) / pdf > 1e-5f) T = mk3(pa.x, pa.y, pa.z) * value / pdf;
                 else alive = false; // exitance = emission only: L already holds it
             }
             used = alive; // this traversal is a cast_ray call the reference makes (raytracer.odin:496)
             if (alive) {
-                const int tri = __float_as_int(h4.w);
-                if (tri < 0) {
+                if (__float_as_int(h4.w) < 0) {
                     // miss: equirectangular env lookup (raytracer.odin:437-446), black without a map
                     if (s.has_env) {
-                        const float tu = 0.5f + atan2f(in_d.z, in_d.x) / TAU_F;
-                        const float tv = 0.5f - asinf(in_d.y) / PI_F;
+                        const float4 d4 = a.qd_in[pos];
+                        const uint32_t slot = __float_as_uint(a.qo_in[pos].w);
+                        const float tu = 0.5f + atan2f(d4.z, d4.x) / TAU_F;
+                        const float tv = 0.5f - asinf(d4.y) / PI_F;
                         const float4 e = texture_sample(s.env, false, tu, tv);
-                        L = L + T * mk3(e.x, e.y, e.z);
+                        const float4 c = a.st_c[slot];
+                        const f3 L = mk3(c.x, c.y, c.z) + T * mk3(e.x, e.y, e.z);
+                        a.st_c[slot] = make_float4(L.x, L.y, L.z, 0.0f);
                     }
-                    st_c[slot] = make_float4(L.x, L.y, L.z, 0.0f);
                 } else {
-                    const float u = h4.y, v = h4.z;
-                    const float4* ts = s.tshade + (size_t)tri * 4;
-                    const float4 s0 = ldg4(ts), s1 = ldg4(ts + 1), s2 = ldg4(ts + 2);
-                    const int4 s3 = __ldg(reinterpret_cast<const int4*>(ts + 3));
-                    const DevMaterial m = s.mats[s3.x];
-                    const float4* tp = s.tris + (size_t)tri * 4;
-                    const float4 ta = ldg4(tp), tb = ldg4(tp + 1), tc = ldg4(tp + 2);
-                    // p = trig.p + trig.u*u + trig.v*v (raytracer.odin:456), individually rounded
-                    const f3 P = mk3(addr(addr(ta.x, mulr(ta.w, u)), mulr(tb.z, v)),
-                                     addr(addr(ta.y, mulr(tb.x, u)), mulr(tb.w, v)),
-                                     addr(addr(ta.z, mulr(tb.y, u)), mulr(tc.x, v)));
-                    const float w0 = 1.0f - u - v;
-                    const bool any_tex = m.color_tex >= 0 || m.emission_tex >= 0 || m.mr_tex >= 0 || m.normal_tex >= 0;
-                    float tcx = 0.0f, tcy = 0.0f;
-                    if (any_tex) {
-                        const float4 uv0 = ldg4(s.tuv + (size_t)tri * 2), uv1 = ldg4(s.tuv + (size_t)tri * 2 + 1);
-                        tcx = uv0.x * w0 + uv0.z * u + uv1.x * v; // raytracer.odin:454
-                        tcy = uv0.y * w0 + uv0.w * u + uv1.y * v;
-                    }
-                    float4 mr = make_float4(1, 1, 1, 1);
-                    if (m.mr_tex >= 0) mr = texture_sample(s.texs[m.mr_tex], false, tcx, tcy);
-                    const f3 n_interp = mk3(s0.x, s0.y, s0.z) * w0 + mk3(s1.x, s1.y, s1.z) * u + mk3(s2.x, s2.y, s2.z) * v;
-                    f3 N;
-                    if (m.normal_tex >= 0) { // raytracer.odin:458-470
-                        const float4* tt = s.ttan + (size_t)tri * 3;
-                        const float4 g0 = ldg4(tt), g1 = ldg4(tt + 1), g2 = ldg4(tt + 2);
-                        float t4x = g0.x * w0 + g1.x * u + g2.x * v, t4y = g0.y * w0 + g1.y * u + g2.y * v;
-                        float t4z = g0.z * w0 + g1.z * u + g2.z * v, t4w = g0.w * w0 + g1.w * u + g2.w * v;
-                        const float l4 = sqrtf(t4x * t4x + t4y * t4y + t4z * t4z + t4w * t4w); // [4]f32 normalize
-                        t4x /= l4; t4y /= l4; t4z /= l4; t4w /= l4;
-                        const f3 lx = mk3(t4x, t4y, t4z);
-                        const f3 lz = normalize3(n_interp);
-                        const f3 ly = cross3(lz, lx) * t4w;
-                        const float4 ns = texture_sample(s.texs[m.normal_tex], false, tcx, tcy);
-                        const f3 ln = mk3(ns.x, ns.y, ns.z) * 2.0f - mk3(1, 1, 1);
-                        N = normalize3(mk3(lx.x * ln.x + ly.x * ln.y + lz.x * ln.z, lx.y * ln.x + ly.y * ln.y + lz.y * ln.z,
-                                           lx.z * ln.x + ly.z * ln.y + lz.z * ln.z));
-                    } else {
-                        N = normalize3(n_interp); // raytracer.odin:472
-                    }
-                    f3 color = mk3(m.color[0], m.color[1], m.color[2]);
-                    f3 emission = mk3(m.emission[0], m.emission[1], m.emission[2]);
-                    if (m.color_tex >= 0) {
-                        const float4 c = texture_sample(s.texs[m.color_tex], true, tcx, tcy);
-                        color = color * mk3(c.x, c.y, c.z);
-                    }
-                    if (m.emission_tex >= 0) {
-                        const float4 c = texture_sample(s.texs[m.emission_tex], true, tcx, tcy);
-                        emission = emission * mk3(c.x, c.y, c.z);
-                    }
-                    const float roughness = omax(m.roughness * mr.y, 0.03f); // raytracer.odin:480
-                    const float metallic = m.metallic * mr.z;
-                    // inside = dot(ng, d) > 0 (raytracer.odin:148), flips the shading normal (:485-488)
-                    const float ngd = addr(addr(mulr(s0.w, in_d.x), mulr(s1.w, in_d.y)), mulr(s2.w, in_d.z));
-                    if (ngd > 0.0f) N = -N;
-                    L = L + T * emission;
-                    bool cont = bounce + 1 < p.ray_depth; // raytrace(.., depth_left - 1) with depth_left == 1 returns 0
-                    f3 nd = mk3(0, 0, 0), value = mk3(0, 0, 0);
-                    float cos_pdf = 0.0f, vndf_term = 0.0f;
-                    if (cont) {
-                        // sample (shading.odin:139-151)
-                        const uint32_t s_local = slot / p.npix, pix = slot - s_local * p.npix;
-                        const uint64_t smp = p.sample_base + s_local;
-                        const Philox4 rr = philox4x32_10(pix, (uint32_t)smp, (uint32_t)(smp >> 32), 1u + (uint32_t)bounce,
-                                                         (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
-                        const float tsel = u01(rr.r0);
-                        if (tsel <= 0.33333f) {
-                            const float phi = u01(rr.r1) * (TAU_F - 0.0f) + 0.0f; // sphere_uniform shading.odin:9-15
-                            const float z = u01(rr.r2) * (1.0f - -1.0f) + -1.0f;
-                            float sx, sy;
-                            sincosf(phi, &sx, &sy);
-                            const float radius = sqrtf(1.0f - sq(z));
-                            nd = normalize3(mk3(sx * radius, sy * radius, z) + N);
-                        } else if (tsel < 0.666666f && has_lights) {
-                            const uint32_t idx = (uint32_t)(((uint64_t)rr.r1 * (uint64_t)(uint32_t)s.n_lights) >> 32);
-                            const float4* lp = s.ltris + (size_t)idx * 4;
-                            const float4 la = ldg4(lp), lb = ldg4(lp + 1), lc = ldg4(lp + 2);
-                            float su = u01(rr.r2) * (1.0f - 0.0f) + 0.0f, sv = u01(rr.r3) * (1.0f - 0.0f) + 0.0f;
-                            if (su + sv > 1.0f) { su = 1.0f - su; sv = 1.0f - sv; }
-                            const f3 world = mk3(la.x, la.y, la.z) + su * mk3(la.w, lb.x, lb.y) + sv * mk3(lb.z, lb.w, lc.x);
-                            nd = normalize3(world - P);
-                        } else {
-                            const f3 hn = vndf_sampling(N, -in_d, sq(roughness), u01(rr.r1), u01(rr.r2));
-                            nd = in_d - 2.0f * dot3(hn, in_d) * hn;
-                        }
-                        value = brdf_cos(color, N, metallic, roughness, in_d, nd);
-                        // norm_l1(value)/pdf > 1e-5 can only hold for norm_l1(value) > 0
-                        if (!(norm_l1(value) > 0.0f)) cont = false;
-                    }
-                    if (cont) {
-                        cos_pdf = omax(dot3(N, nd) / PI_F, 0.0f); // shading.odin:37-39
-                        vndf_term = vndf_sampling_pdf(N, -in_d, sq(roughness), nd) * (has_lights ? 1.0f : 2.0f);
-                        st_a[slot] = make_float4(T.x, T.y, T.z, cos_pdf);
-                        st_b[slot] = make_float4(value.x, value.y, value.z, vndf_term);
-                        emit = true;
-                        out_o = make_float4(P.x, P.y, P.z, o4.w);
-                        out_d = make_float4(nd.x, nd.y, nd.z, 0.0f);
-                    }
-                    st_c[slot] = make_float4(L.x, L.y, L.z, 0.0f);
+                    heavy = true;
                 }
             }
         }
         const unsigned umask = __ballot_sync(0xffffffffu, used);
-        if (umask && lane == 0) atomicAdd(used_ptr, (uint32_t)__popc(umask));
-        if (bin_octants) {
+        if (umask && lane == 0) atomicAdd(a.used_ptr, (uint32_t)__popc(umask));
+        // ---- append the work items to the block's queue; phase B runs once 256 are pending (or at
+        //      the very end), so every warp of the block shades a full complement of hits
+        const unsigned hmask = __ballot_sync(0xffffffffu, heavy);
+        if (threadIdx.x < 16) s_cnt[threadIdx.x] = 0u;
+        if (lane == 0) s_wsum[wid] = (uint32_t)__popc(hmask);
+        __syncthreads();
+        uint32_t wbase = 0, n_new = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+            const uint32_t c = s_wsum[w];
+            if (w < wid) wbase += c;
+            n_new += c;
+        }
+        uint32_t qn = s_qn; // < 256 here
+        if (heavy) s_q[qn + wbase + __popc(hmask & ((1u << lane) - 1u))] = make_float4(T.x, T.y, T.z, __uint_as_float(pos));
+        qn += n_new;
+        __syncthreads();
+        const bool run_b = qn >= 256u || (!more && qn > 0u);
+        const uint32_t n_work = run_b ? (qn < 256u ? qn : 256u) : 0u;
+        const uint32_t q_first = qn - n_work; // the newest n_work items are taken
+        if (!run_b) {
+            if (threadIdx.x == 0) s_qn = qn;
+            __syncthreads();
+            if (!more) break;
+            continue;
+        }
+
+        // ---- phase B: dense warps shade the hits
+        bool emit = false;
+        float4 out_o = make_float4(0, 0, 0, 0), out_d = make_float4(0, 0, 0, 0);
+        float4 out_a = make_float4(0, 0, 0, 0), out_b = make_float4(0, 0, 0, 0);
+        if (threadIdx.x < n_work) {
+            const float4 w4 = s_q[q_first + threadIdx.x];
+            const uint32_t wpos = __float_as_uint(w4.w);
+            T = mk3(w4.x, w4.y, w4.z);
+            const float4 o4 = a.qo_in[wpos];
+            const float4 d4 = a.qd_in[wpos];
+            const float4 h4 = a.hits[wpos];
+            const uint32_t slot = __float_as_uint(o4.w);
+            const f3 in_d = mk3(d4.x, d4.y, d4.z);
+            const int tri = __float_as_int(h4.w);
+            const float u = h4.y, v = h4.z;
+            const float4* ts = s.tshade + (size_t)tri * 4;
+            const float4 s0 = ldg4(ts), s1 = ldg4(ts + 1), s2 = ldg4(ts + 2);
+            const int4 s3 = __ldg(reinterpret_cast<const int4*>(ts + 3));
+            const DevMaterial m = s.mats[s3.x];
+            const float4* tp = s.tris + (size_t)tri * 4;
+            const float4 ta = ldg4(tp), tb = ldg4(tp + 1), tc = ldg4(tp + 2);
+            // p = trig.p + trig.u*u + trig.v*v (raytracer.odin:456), individually rounded
+            const f3 P = mk3(addr(addr(ta.x, mulr(ta.w, u)), mulr(tb.z, v)),
+                             addr(addr(ta.y, mulr(tb.x, u)), mulr(tb.w, v)),
+                             addr(addr(ta.z, mulr(tb.y, u)), mulr(tc.x, v)));
+            const float w0 = 1.0f - u - v;
+            const bool any_tex = m.color_tex >= 0 || m.emission_tex >= 0 || m.mr_tex >= 0 || m.normal_tex >= 0;
+            float tcx = 0.0f, tcy = 0.0f;
+            if (any_tex) {
+                const float4 uv0 = ldg4(s.tuv + (size_t)tri * 2), uv1 = ldg4(s.tuv + (size_t)tri * 2 + 1);
+                tcx = uv0.x * w0 + uv0.z * u + uv1.x * v; // raytracer.odin:454
+                tcy = uv0.y * w0 + uv0.w * u + uv1.y * v;
+            }
+            float4 mr = make_float4(1, 1, 1, 1);
+            if (m.mr_tex >= 0) mr = texture_sample(s.texs[m.mr_tex], false, tcx, tcy);
+            const f3 n_interp = mk3(s0.x, s0.y, s0.z) * w0 + mk3(s1.x, s1.y, s1.z) * u + mk3(s2.x, s2.y, s2.z) * v;
+            f3 N;
+            if (m.normal_tex >= 0) { // raytracer.odin:458-470
+                const float4* tt = s.ttan + (size_t)tri * 3;
+                const float4 g0 = ldg4(tt), g1 = ldg4(tt + 1), g2 = ldg4(tt + 2);
+                float t4x = g0.x * w0 + g1.x * u + g2.x * v, t4y = g0.y * w0 + g1.y * u + g2.y * v;
+                float t4z = g0.z * w0 + g1.z * u + g2.z * v, t4w = g0.w * w0 + g1.w * u + g2.w * v;
+                const float l4 = sqrtf(t4x * t4x + t4y * t4y + t4z * t4z + t4w * t4w); // [4]f32 normalize
+                t4x /= l4; t4y /= l4; t4z /= l4; t4w /= l4;
+                const f3 lx = mk3(t4x, t4y, t4z);
+                const f3 lz = normalize3(n_interp);
+                const f3 ly = cross3(lz, lx) * t4w;
+                const float4 ns = texture_sample(s.texs[m.normal_tex], false, tcx, tcy);
+                const f3 ln = mk3(ns.x, ns.y, ns.z) * 2.0f - mk3(1, 1, 1);
+                N = normalize3(mk3(lx.x * ln.x + ly.x * ln.y + lz.x * ln.z, lx.y * ln.x + ly.y * ln.y + lz.y * ln.z,
+                                   lx.z * ln.x + ly.z * ln.y + lz.z * ln.z));
+            } else {
+                N = normalize3(n_interp); // raytracer.odin:472
+            }
+            f3 color = mk3(m.color[0], m.color[1], m.color[2]);
+            f3 emission = mk3(m.emission[0], m.emission[1], m.emission[2]);
+            if (m.color_tex >= 0) {
+                const float4 c = texture_sample(s.texs[m.color_tex], true, tcx, tcy);
+                color = color * mk3(c.x, c.y, c.z);
+            }
+            if (m.emission_tex >= 0) {
+                const float4 c = texture_sample(s.texs[m.emission_tex], true, tcx, tcy);
+                emission = emission * mk3(c.x, c.y, c.z);
+            }
+            const float roughness = omax(m.roughness * mr.y, 0.03f); // raytracer.odin:480
+            const float metallic = m.metallic * mr.z;
+            // inside = dot(ng, d) > 0 (raytracer.odin:148), flips the shading normal (:485-488)
+            const float ngd = addr(addr(mulr(s0.w, in_d.x), mulr(s1.w, in_d.y)), mulr(s2.w, in_d.z));
+            if (ngd > 0.0f) N = -N;
+            // L = L + T * emission: the accumulator is only touched when this hit emits (adding an
+            // exact zero would leave it unchanged)
+            if (emission.x != 0.0f || emission.y != 0.0f || emission.z != 0.0f) {
+                const float4 c = a.st_c[slot];
+                const f3 L = mk3(c.x, c.y, c.z) + T * emission;
+                a.st_c[slot] = make_float4(L.x, L.y, L.z, 0.0f);
+            }
+            bool cont = bounce + 1 < p.ray_depth; // raytrace(.., depth_left - 1) with depth_left == 1 returns 0
+            f3 nd = mk3(0, 0, 0), value = mk3(0, 0, 0);
+            if (cont) {
+                // sample (shading.odin:139-151)
+                const uint32_t s_local = slot / p.npix, pix = slot - s_local * p.npix;
+                const uint64_t smp = p.sample_base + s_local;
+                const Philox4 rr = philox4x32_10(pix, (uint32_t)smp, (uint32_t)(smp >> 32), 1u + (uint32_t)bounce,
+                                                 (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+                const float tsel = u01(rr.r0);
+                if (tsel <= 0.33333f) {
+                    const float phi = u01(rr.r1) * (TAU_F - 0.0f) + 0.0f; // sphere_uniform shading.odin:9-15
+                    const float z = u01(rr.r2) * (1.0f - -1.0f) + -1.0f;
+                    float sx, sy;
+                    sincosf(phi, &sx, &sy);
+                    const float radius = sqrtf(1.0f - sq(z));
+                    nd = normalize3(mk3(sx * radius, sy * radius, z) + N);
+                } else if (tsel < 0.666666f && has_lights) {
+                    const uint32_t idx = (uint32_t)(((uint64_t)rr.r1 * (uint64_t)(uint32_t)s.n_lights) >> 32);
+                    const float4* lp = s.ltris + (size_t)idx * 4;
+                    const float4 la = ldg4(lp), lb = ldg4(lp + 1), lc = ldg4(lp + 2);
+                    float su = u01(rr.r2) * (1.0f - 0.0f) + 0.0f, sv = u01(rr.r3) * (1.0f - 0.0f) + 0.0f;
+                    if (su + sv > 1.0f) { su = 1.0f - su; sv = 1.0f - sv; }
+                    const f3 world = mk3(la.x, la.y, la.z) + su * mk3(la.w, lb.x, lb.y) + sv * mk3(lb.z, lb.w, lc.x);
+                    nd = normalize3(world - P);
+                } else {
+                    const f3 hn = vndf_sampling(N, -in_d, sq(roughness), u01(rr.r1), u01(rr.r2));
+                    nd = in_d - 2.0f * dot3(hn, in_d) * hn;
+                }
+                value = brdf_cos(color, N, metallic, roughness, in_d, nd);
+                // norm_l1(value)/pdf > 1e-5 can only hold for norm_l1(value) > 0
+                if (!(norm_l1(value) > 0.0f)) cont = false;
+            }
+            if (cont) {
+                const float cos_pdf = omax(dot3(N, nd) / PI_F, 0.0f); // shading.odin:37-39
+                const float vndf_term = vndf_sampling_pdf(N, -in_d, sq(roughness), nd) * (has_lights ? 1.0f : 2.0f);
+                emit = true;
+                out_a = make_float4(T.x, T.y, T.z, cos_pdf);
+                out_b = make_float4(value.x, value.y, value.z, vndf_term);
+                out_o = make_float4(P.x, P.y, P.z, o4.w);
+                out_d = make_float4(nd.x, nd.y, nd.z, 0.0f);
+            }
+        }
+        if (a.bin_octants) {
             // Queue compaction per BLOCK with an 8-bin counting sort on the direction octant: the 256
             // paths of this iteration come from neighbouring pixels, so each run in the queue holds
             // rays with nearby origins AND the same direction signs.  Rays fetched together by a
             // traversal warp then share nodes (one L1 wavefront serves several lanes) and child order.
-            if (threadIdx.x < 16) s_cnt[threadIdx.x] = 0u;
-            __syncthreads();
             const int oct = (out_d.x < 0.0f ? 1 : 0) | (out_d.y < 0.0f ? 2 : 0) | (out_d.z < 0.0f ? 4 : 0);
             bool cand = emit && has_lights;
-            if (cand && prefilter && !light_root_hit(s, out_o, out_d)) cand = false;
+            if (cand && a.prefilter && !light_root_hit(s, out_o, out_d)) cand = false;
             uint32_t rank = 0, lrank = 0;
             if (emit) rank = atomicAdd(&s_cnt[oct], 1u);
             if (cand) lrank = atomicAdd(&s_cnt[8 + oct], 1u);
@@ -495,49 +556,59 @@ k_shade(const SceneDev s, const RenderParams p, const int bounce, const float4* 
             if (threadIdx.x == 0) {
                 uint32_t tot = 0, ltot = 0;
                 for (int i = 0; i < 8; i++) { tot += s_cnt[i]; ltot += s_cnt[8 + i]; }
-                uint32_t b0 = tot ? atomicAdd(n_out_ptr, tot) : 0u;
-                uint32_t b1 = ltot ? atomicAdd(lq_count, ltot) : 0u;
+                uint32_t b0 = tot ? atomicAdd(a.n_out_ptr, tot) : 0u;
+                uint32_t b1 = ltot ? atomicAdd(a.lq_count, ltot) : 0u;
                 for (int i = 0; i < 8; i++) { s_off[i] = b0; b0 += s_cnt[i]; s_off[8 + i] = b1; b1 += s_cnt[8 + i]; }
             }
             __syncthreads();
             if (emit) {
                 const uint32_t q = s_off[oct] + rank;
-                qo_out[q] = out_o;
-                qd_out[q] = out_d;
+                a.qo_out[q] = out_o;
+                a.qd_out[q] = out_d;
+                a.pa_out[q] = out_a;
+                a.pb_out[q] = out_b;
                 if (has_lights) {
-                    if (cand) lq[s_off[8 + oct] + lrank] = q;
-                    else lsum_out[q] = 0.0f;
+                    if (cand) a.lq[s_off[8 + oct] + lrank] = q;
+                    else a.lsum_out[q] = 0.0f;
                 }
             }
+            if (threadIdx.x == 0) s_qn = q_first;
+            __syncthreads(); // s_cnt / s_off / s_q / s_qn are reused by the next iteration
+            if (!more && q_first == 0u) break;
             continue;
         }
         // queue compaction: warp ballot + prefix popcount + one atomic per warp
         const unsigned mask = __ballot_sync(0xffffffffu, emit);
         if (mask) {
             const int leader = __ffs(mask) - 1;
-            uint32_t wbase = 0;
-            if (lane == leader) wbase = atomicAdd(n_out_ptr, (uint32_t)__popc(mask));
-            wbase = __shfl_sync(0xffffffffu, wbase, leader);
+            uint32_t qbase = 0;
+            if (lane == leader) qbase = atomicAdd(a.n_out_ptr, (uint32_t)__popc(mask));
+            qbase = __shfl_sync(0xffffffffu, qbase, leader);
             uint32_t q = 0;
             if (emit) {
-                q = wbase + __popc(mask & ((1u << lane) - 1u));
-                qo_out[q] = out_o;
-                qd_out[q] = out_d;
+                q = qbase + __popc(mask & ((1u << lane) - 1u));
+                a.qo_out[q] = out_o;
+                a.qd_out[q] = out_d;
+                a.pa_out[q] = out_a;
+                a.pb_out[q] = out_b;
             }
             if (has_lights) {
                 // second queue: only rays that can reach a light need the light-BVH pass
                 bool cand = emit;
-                if (emit && prefilter && !light_root_hit(s, out_o, out_d)) { cand = false; lsum_out[q] = 0.0f; }
+                if (emit && a.prefilter && !light_root_hit(s, out_o, out_d)) { cand = false; a.lsum_out[q] = 0.0f; }
                 const unsigned cmask = __ballot_sync(0xffffffffu, cand);
                 if (cmask) {
                     const int cl = __ffs(cmask) - 1;
                     uint32_t cbase = 0;
-                    if (lane == cl) cbase = atomicAdd(lq_count, (uint32_t)__popc(cmask));
+                    if (lane == cl) cbase = atomicAdd(a.lq_count, (uint32_t)__popc(cmask));
                     cbase = __shfl_sync(0xffffffffu, cbase, cl);
-                    if (cand) lq[cbase + __popc(cmask & ((1u << lane) - 1u))] = q;
+                    if (cand) a.lq[cbase + __popc(cmask & ((1u << lane) - 1u))] = q;
                 }
             }
         }
+        if (threadIdx.x == 0) s_qn = q_first;
+        __syncthreads(); // s_q / s_qn / s_wsum are reused by the next iteration
+        if (!more && q_first == 0u) break;
     }
 }
 

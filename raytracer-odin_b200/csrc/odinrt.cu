@@ -63,7 +63,8 @@ struct ort_ctx {
         float4* hits = nullptr;
         float* lsum = nullptr;  // 2 x capacity floats: ping-pong by bounce parity
         uint32_t* lq = nullptr; // light-candidate queue (positions into the ray queue)
-        float4 *st_a = nullptr, *st_b = nullptr, *st_c = nullptr;
+        float4 *pa[2] = {nullptr, nullptr}, *pb[2] = {nullptr, nullptr}; // pending (T, value, pdf terms), queue order
+        float4* st_c = nullptr;                                           // accumulated radiance by path slot
         uint32_t* counters = nullptr; // 5 arrays of D+2: queue counts, trace / light work counters, used-ray counts, light-queue counts
         int64_t capacity = 0;
         int counters_depth = 0;
@@ -144,9 +145,9 @@ void free_scene(ort_ctx* c) { // only at destroy: uploads recycle the pools
 }
 void free_paths(ort_ctx* c) {
     for (auto& P : c->ps) {
-        void* ptrs[] = {P.qo[0], P.qo[1], P.qd[0], P.qd[1], P.hits, P.lsum, P.lq, P.st_a, P.st_b, P.st_c};
+        void* ptrs[] = {P.qo[0], P.qo[1], P.qd[0], P.qd[1], P.hits, P.lsum, P.lq, P.pa[0], P.pa[1], P.pb[0], P.pb[1], P.st_c};
         for (void* p : ptrs) if (p) cudaFree(p);
-        P.qo[0] = P.qo[1] = P.qd[0] = P.qd[1] = P.hits = P.st_a = P.st_b = P.st_c = nullptr;
+        P.qo[0] = P.qo[1] = P.qd[0] = P.qd[1] = P.hits = P.pa[0] = P.pa[1] = P.pb[0] = P.pb[1] = P.st_c = nullptr;
         P.lsum = nullptr; P.lq = nullptr;
         P.capacity = 0;
     }
@@ -285,23 +286,25 @@ int ensure_paths(ort_ctx* ctx, int64_t need, int pipes = 1) {
     for (int i = 0; i < pipes; i++) {
         auto& P = ctx->ps[i];
         if (P.capacity >= need) continue;
-        void* ptrs[] = {P.qo[0], P.qo[1], P.qd[0], P.qd[1], P.hits, P.lsum, P.lq, P.st_a, P.st_b, P.st_c};
+        void* ptrs[] = {P.qo[0], P.qo[1], P.qd[0], P.qd[1], P.hits, P.lsum, P.lq, P.pa[0], P.pa[1], P.pb[0], P.pb[1], P.st_c};
         for (void* p : ptrs) if (p) cudaFree(p);
-        ctx->path_bytes -= P.capacity * (16 * 8 + 12);
+        P.qo[0] = P.qo[1] = P.qd[0] = P.qd[1] = P.hits = P.pa[0] = P.pa[1] = P.pb[0] = P.pb[1] = P.st_c = nullptr;
+        P.lsum = nullptr; P.lq = nullptr;
+        ctx->path_bytes -= P.capacity * (16 * 10 + 12);
         P.capacity = 0;
         const size_t n = (size_t)need;
         for (int k = 0; k < 2; k++) {
             CK(cudaMalloc(&P.qo[k], n * 16));
             CK(cudaMalloc(&P.qd[k], n * 16));
+            CK(cudaMalloc(&P.pa[k], n * 16));
+            CK(cudaMalloc(&P.pb[k], n * 16));
         }
         CK(cudaMalloc(&P.hits, n * 16));
         CK(cudaMalloc(&P.lsum, n * 8));
         CK(cudaMalloc(&P.lq, n * 4));
-        CK(cudaMalloc(&P.st_a, n * 16));
-        CK(cudaMalloc(&P.st_b, n * 16));
         CK(cudaMalloc(&P.st_c, n * 16));
         P.capacity = need;
-        ctx->path_bytes += (int64_t)(n * (16 * 8 + 12));
+        ctx->path_bytes += (int64_t)(n * (16 * 10 + 12));
     }
     return 0;
 }
@@ -396,6 +399,8 @@ int launch_wave(ort_ctx* ctx, ort_ctx::PathSet& P, cudaStream_t st, cudaEvent_t 
     {
         Prof pr(ctx, &ctx->ms_other);
         CK(cudaMemsetAsync(P.counters, 0, sizeof(uint32_t) * 5 * (size_t)(D + 2), st));
+        // L = 0: k_shade only touches the accumulator of a path when a hit adds radiance
+        CK(cudaMemsetAsync(P.st_c, 0, (size_t)p.n_batch_samples * p.npix * 16, st));
         k_raygen<<<ctx->shade_grid, 256, 0, st>>>(p, P.qo[0], P.qd[0], counts);
         ctx->launches++;
     }
@@ -415,9 +420,14 @@ int launch_wave(ort_ctx* ctx, ort_ctx::PathSet& P, cudaStream_t st, cudaEvent_t 
         }
         {
             Prof pr(ctx, &ctx->ms_shade);
-            k_shade<<<ctx->shade_grid, 256, 0, st>>>(ctx->sd, p, k, P.qo[in], P.qd[in], P.hits, lsum_in, counts + k,
-                                                     P.qo[out], P.qd[out], counts + k + 1, used + k, P.st_a, P.st_b, P.st_c,
-                                                     lsum_out, P.lq, lcount + k + 1, ctx->fuse ? 0 : prefilter, ctx->bin_octants);
+            ShadeArgs sa;
+            sa.qo_in = P.qo[in]; sa.qd_in = P.qd[in]; sa.hits = P.hits; sa.pa_in = P.pa[in]; sa.pb_in = P.pb[in];
+            sa.lsum = lsum_in; sa.n_in_ptr = counts + k;
+            sa.qo_out = P.qo[out]; sa.qd_out = P.qd[out]; sa.pa_out = P.pa[out]; sa.pb_out = P.pb[out];
+            sa.n_out_ptr = counts + k + 1; sa.used_ptr = used + k; sa.st_c = P.st_c;
+            sa.lsum_out = lsum_out; sa.lq = P.lq; sa.lq_count = lcount + k + 1;
+            sa.bounce = k; sa.prefilter = ctx->fuse ? 0 : prefilter; sa.bin_octants = ctx->bin_octants;
+            k_shade<<<ctx->shade_grid, 256, 0, st>>>(ctx->sd, p, sa);
             ctx->launches++;
         }
     }
