@@ -329,7 +329,8 @@ def main():
         else:
             bpr = None
         trace_s = ps["trace_ms"] * 1e-3
-        spp_per_wave = max(1, (1 << 24) // npix)  # library default: 2^24 paths per wave
+        wave_paths = int(os.environ.get("ORT_WAVE_PATHS", 1 << 25))  # library default: 2^25 paths per wave
+        spp_per_wave = max(1, wave_paths // npix)
         n_launch = depth * ((spp + spp_per_wave - 1) // spp_per_wave)  # one k_trace<closest> per bounce per wave
         traffic = None
         tpath = os.path.join(ROOT, "profiles", f"ncu_traffic_{args.config.lower()}.json")

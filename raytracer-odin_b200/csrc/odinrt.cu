@@ -450,7 +450,7 @@ int render_impl(ort_ctx* ctx, uint32_t w, uint32_t h, int32_t depth, uint64_t fi
     if (depth < 0) return fail(ctx, "ray_depth must be >= 0");
     const uint64_t npix = (uint64_t)w * h;
     if (npix > (1ull << 31)) return fail(ctx, "image too large");
-    int64_t cap = ctx->capacity_cfg > 0 ? ctx->capacity_cfg : ((int64_t)1 << 24); // paths per wave (x up to 4 overlapped waves)
+    int64_t cap = ctx->capacity_cfg > 0 ? ctx->capacity_cfg : ((int64_t)1 << 25); // paths per wave (x up to 4 overlapped waves)
     if ((uint64_t)cap < npix) cap = (int64_t)npix;
     uint64_t per_wave = std::max<uint64_t>(1, (uint64_t)cap / npix);
     if (per_wave > n_samples) per_wave = std::max<uint64_t>(n_samples, 1);
