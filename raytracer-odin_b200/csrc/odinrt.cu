@@ -85,6 +85,7 @@ struct ort_ctx {
     int trace_grid[2][3] = {{0, 0, 0}, {0, 0, 0}}; // [node encoding][mode] persistent grid sizes
     int shade_grid = 0;
     bool quant = false; // scene uses QuantNode
+    int exp_ctas = 0; // env ORT_EXP_CTAS=n: occupancy experiment, at most n traversal CTAs per SM
     int fuse = 0; // env ORT_FUSE=1: trace closest hit + light sum in one fused pass
     int bin_octants = 1;     // env ORT_BIN=0: plain per-warp queue compaction (no direction-octant binning)
     int light_prefilter = 1; // env ORT_LIGHT_PREFILTER=0: send every continuation ray through the light pass
@@ -344,10 +345,13 @@ void launch_trace(ort_ctx* ctx, ort_ctx::PathSet& P, cudaStream_t st, const floa
     a.qo = qo; a.qd = qd; a.n_ptr = n_ptr; a.work_ctr = work_ctr; a.index = index;
     a.hits = P.hits; a.lsum = lsum ? lsum : P.lsum;
     a.refill_threshold = ctx->refill; a.inner_min = ctx->inner_min;
-    const int g = ctx->trace_grid[ctx->quant ? 1 : 0][mode];
+    int g = ctx->trace_grid[ctx->quant ? 1 : 0][mode];
+    // sensitivity experiment (ORT_EXP_CTAS=n): cap the resident CTAs per SM with unused dynamic shared memory
+    const size_t dsm = ctx->exp_ctas > 0 ? (size_t)(200 * 1024 / ctx->exp_ctas - 17 * 1024) : 0;
+    if (ctx->exp_ctas > 0) g = std::min(g, ctx->sm_count * ctx->exp_ctas);
     if (!ctx->quant) {
-        if (mode == 0) k_trace<true, false, false><<<g, TRACE_THREADS, 0, st>>>(ctx->sd, a);
-        else if (mode == 1) k_trace<false, true, false><<<g, TRACE_THREADS, 0, st>>>(ctx->sd, a);
+        if (mode == 0) k_trace<true, false, false><<<g, TRACE_THREADS, dsm, st>>>(ctx->sd, a);
+        else if (mode == 1) k_trace<false, true, false><<<g, TRACE_THREADS, dsm, st>>>(ctx->sd, a);
         else k_trace<true, true, false><<<g, TRACE_THREADS, 0, st>>>(ctx->sd, a);
     } else {
         if (mode == 0) k_trace<true, false, true><<<g, TRACE_THREADS, 0, st>>>(ctx->sd, a);
@@ -563,6 +567,14 @@ int ort_create(ort_ctx** out, const ort_device_cfg* cfg) {
     if (const char* e2 = std::getenv("ORT_REFILL")) c->refill = std::atoi(e2);
     if (const char* e2 = std::getenv("ORT_INNER_MIN")) c->inner_min = std::atoi(e2);
     if (const char* e2 = std::getenv("ORT_FUSE")) c->fuse = std::atoi(e2);
+    if (const char* e2 = std::getenv("ORT_EXP_CTAS")) {
+        c->exp_ctas = std::atoi(e2);
+        if (c->exp_ctas > 0) {
+            const int bytes = 200 * 1024 / c->exp_ctas - 17 * 1024;
+            cudaFuncSetAttribute(k_trace<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+            cudaFuncSetAttribute(k_trace<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        }
+    }
     if (const char* e2 = std::getenv("ORT_LIGHT_PREFILTER")) c->light_prefilter = std::atoi(e2);
     if (const char* e2 = std::getenv("ORT_BIN")) c->bin_octants = std::atoi(e2);
     ctx = c;
