@@ -264,6 +264,103 @@ bool build_wide_bvh(const ort_bvh_node* bvh, int64_t n_nodes, int64_t n_tris, Wi
     return true;
 }
 
+bool build_wide8_bvh(const ort_bvh_node* bvh, int64_t n_nodes, int64_t n_tris, Wide8BVH* out, const char** err) {
+    out->nodes.clear();
+    out->tri_order.clear();
+    out->depth = 0;
+    if (n_nodes <= 0) { *err = "empty BVH node array"; return false; }
+    out->tri_order.reserve((size_t)n_tris);
+    struct Pending { int64_t src; uint32_t dst; int level; };
+    std::vector<Pending> queue;
+    out->nodes.emplace_back();
+    queue.push_back({n_nodes - 1, 0u, 1});
+    auto area = [&](int64_t id) {
+        const ort_bvh_node& nd = bvh[id];
+        float sx = nd.hi[0] - nd.lo[0], sy = nd.hi[1] - nd.lo[1], sz = nd.hi[2] - nd.lo[2];
+        float a = sx * sy + sy * sz + sz * sx;
+        return std::isfinite(a) ? a : 0.0f;
+    };
+    for (size_t qi = 0; qi < queue.size(); qi++) {
+        const Pending cur = queue[qi];
+        if (cur.level > out->depth) out->depth = cur.level;
+        int64_t kids[8];
+        int nk = 0;
+        if (bvh[cur.src].kind == 0) {
+            if (bvh[cur.src].b > 0) kids[nk++] = cur.src; // a lone (root) leaf
+        } else {
+            kids[nk++] = bvh[cur.src].a;
+            kids[nk++] = bvh[cur.src].b;
+            while (nk < 8) { // open the largest inner child until the node is full
+                int pick = -1;
+                float best = -1.0f;
+                for (int i = 0; i < nk; i++)
+                    if (bvh[kids[i]].kind == 1 && area(kids[i]) > best) { best = area(kids[i]); pick = i; }
+                if (pick < 0) break;
+                const int64_t open = kids[pick];
+                kids[pick] = bvh[open].a;
+                kids[nk++] = bvh[open].b;
+            }
+        }
+        // slot assignment: greedy maximum of dot(child centre - node centre, slot direction)
+        int slot_of[8], kid_at[8];
+        for (int i = 0; i < 8; i++) { slot_of[i] = -1; kid_at[i] = -1; }
+        {
+            const ort_bvh_node& pn = bvh[cur.src];
+            float pc[3], cost[8][8];
+            for (int ax = 0; ax < 3; ax++) pc[ax] = 0.5f * (pn.lo[ax] + pn.hi[ax]);
+            for (int i = 0; i < nk; i++) {
+                const ort_bvh_node& c = bvh[kids[i]];
+                float d[3];
+                for (int ax = 0; ax < 3; ax++) {
+                    d[ax] = 0.5f * (c.lo[ax] + c.hi[ax]) - pc[ax];
+                    if (!std::isfinite(d[ax])) d[ax] = 0.0f;
+                }
+                for (int sl = 0; sl < 8; sl++)
+                    cost[i][sl] = ((sl & 1) ? d[0] : -d[0]) + ((sl & 2) ? d[1] : -d[1]) + ((sl & 4) ? d[2] : -d[2]);
+            }
+            for (int round = 0; round < nk; round++) {
+                int bi = -1, bs = -1;
+                float bc = -kInf;
+                for (int i = 0; i < nk; i++) {
+                    if (slot_of[i] >= 0) continue;
+                    for (int sl = 0; sl < 8; sl++)
+                        if (kid_at[sl] < 0 && cost[i][sl] > bc) { bc = cost[i][sl]; bi = i; bs = sl; }
+                }
+                slot_of[bi] = bs;
+                kid_at[bs] = bi;
+            }
+        }
+        Wide8Node wn;
+        std::memset(&wn, 0, sizeof wn);
+        for (int sl = 0; sl < 8; sl++)
+            for (int ax = 0; ax < 3; ax++) { wn.bounds[ax][0][sl] = kInf; wn.bounds[ax][1][sl] = -kInf; }
+        wn.child_base = (uint32_t)out->nodes.size();
+        wn.tri_base = (uint32_t)out->tri_order.size();
+        uint32_t tri_off = 0;
+        for (int sl = 0; sl < 8; sl++) {
+            if (kid_at[sl] < 0) continue;
+            const ort_bvh_node& c = bvh[kids[kid_at[sl]]];
+            if (c.kind == 0 && c.b == 0) continue; // empty leaf: slot stays unused
+            for (int ax = 0; ax < 3; ax++) { wn.bounds[ax][0][sl] = c.lo[ax]; wn.bounds[ax][1][sl] = c.hi[ax]; }
+            if (c.kind == 0) {
+                if (c.a < 0 || c.b < 0 || c.a + c.b > n_tris) { *err = "BVH leaf out of range (first/count)"; return false; }
+                if (tri_off + (uint32_t)c.b > 32u) { *err = "8-wide node would reference more than 32 triangles"; return false; }
+                wn.trimask[sl] = (uint32_t)((((uint64_t)1 << c.b) - 1) << tri_off);
+                for (int64_t t = 0; t < c.b; t++) out->tri_order.push_back((uint32_t)(c.a + t));
+                tri_off += (uint32_t)c.b;
+            } else {
+                if (out->nodes.size() >= (size_t)0x7fffffff) { *err = "wide BVH too large"; return false; }
+                wn.imask |= 1u << sl;
+                const uint32_t dst = (uint32_t)out->nodes.size();
+                out->nodes.emplace_back();
+                queue.push_back({kids[kid_at[sl]], dst, cur.level + 1});
+            }
+        }
+        out->nodes[cur.dst] = wn;
+    }
+    return true;
+}
+
 void quantize_wide_nodes(const WideNode* in, size_t n, QuantNode* out) {
     for (size_t i = 0; i < n; i++) {
         const WideNode& w = in[i];

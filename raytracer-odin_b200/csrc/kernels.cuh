@@ -24,6 +24,9 @@ constexpr float TAU_F = 6.28318530717958647692528676655900576f;
 #ifndef ORT_TRACE_MIN_CTAS
 #define ORT_TRACE_MIN_CTAS 1
 #endif
+#ifndef ORT_TRACE8_MIN_CTAS
+#define ORT_TRACE8_MIN_CTAS 1
+#endif
 constexpr int TRACE_THREADS = 128;
 constexpr int SMEM_STACK = ORT_SMEM_STACK;        // stack entries per thread kept in shared memory
 constexpr int LOCAL_STACK = 128 - ORT_SMEM_STACK; // overflow entries per thread in local memory
@@ -57,6 +60,11 @@ struct SceneDev {
     int32_t has_env;
     int32_t n_lights;
     float pad_scale[3];  // max |coordinate| of the scene root box (light triangles are scene triangles)
+    // 8-wide re-emission (traverse8.cuh): Wide8Node[], 16 float4 each, scene tree (root 0) then light tree;
+    // TriIsect[] in TRAVERSAL order (pad[0] = reference triangle index), scene then light triangles
+    const float4* nodes8;
+    const float4* tris8;
+    int32_t light_root8;
 };
 
 struct RenderParams {
@@ -152,6 +160,7 @@ __device__ __forceinline__ bool tri_uv(const RaySetup& r, float4 a, float4 b, fl
 
 } // namespace ort
 #include "traverse.cuh"
+#include "traverse8.cuh"
 namespace ort {
 
 // ------------------------------------------------------------------------------------------------

@@ -42,7 +42,7 @@ struct ort_ctx {
     // re-uploading a scene of the same shape performs no cudaMalloc / cudaFree (a cudaFree was
     // measured at 15-600 ms on B200 boxes: it synchronises the device and unmaps).
     struct DevBuf { void* p = nullptr; size_t cap = 0, used = 0; };
-    enum { SB_NODES, SB_TRIS, SB_LLIGHT, SB_MATS, SB_TSHADE, SB_TUV, SB_TTAN, SB_TEXS, SB_COUNT };
+    enum { SB_NODES, SB_TRIS, SB_LLIGHT, SB_MATS, SB_TSHADE, SB_TUV, SB_TTAN, SB_TEXS, SB_NODES8, SB_TRIS8, SB_COUNT };
     DevBuf sbuf[SB_COUNT];
     struct TexSlot { cudaArray_t arr = nullptr; cudaTextureObject_t obj = 0; size_t w = 0, h = 0; bool in_use = false; };
     std::vector<TexSlot> tex_pool;
@@ -55,6 +55,10 @@ struct ort_ctx {
     int host_threads = 1;
     int64_t n_tris = 0, n_ltris = 0;
     WideBVH wide, lwide;
+    Wide8BVH wide8, lwide8;
+    int bvh8 = 0;      // env ORT_BVH8=1: traverse the 8-wide re-emission (k_trace8)
+    bool use8 = false; // the uploaded scene has an 8-wide tree
+    int trace8_grid[2] = {0, 0};
     int64_t scene_bytes = 0;
 
     // path buffers: two independent wave pipelines (ps[1] only when waves are overlapped)
@@ -345,6 +349,12 @@ void launch_trace(ort_ctx* ctx, ort_ctx::PathSet& P, cudaStream_t st, const floa
     a.qo = qo; a.qd = qd; a.n_ptr = n_ptr; a.work_ctr = work_ctr; a.index = index;
     a.hits = P.hits; a.lsum = lsum ? lsum : P.lsum;
     a.refill_threshold = ctx->refill; a.inner_min = ctx->inner_min;
+    if (ctx->use8 && mode < 2) {
+        if (mode == 0) k_trace8<true><<<ctx->trace8_grid[0], TRACE_THREADS, 0, st>>>(ctx->sd, a);
+        else k_trace8<false><<<ctx->trace8_grid[1], TRACE_THREADS, 0, st>>>(ctx->sd, a);
+        ctx->launches++;
+        return;
+    }
     int g = ctx->trace_grid[ctx->quant ? 1 : 0][mode];
     // sensitivity experiment (ORT_EXP_CTAS=n): cap the resident CTAs per SM with unused dynamic shared memory
     const size_t dsm = ctx->exp_ctas > 0 ? (size_t)(200 * 1024 / ctx->exp_ctas - 17 * 1024) : 0;
@@ -567,6 +577,7 @@ int ort_create(ort_ctx** out, const ort_device_cfg* cfg) {
     if (const char* e2 = std::getenv("ORT_REFILL")) c->refill = std::atoi(e2);
     if (const char* e2 = std::getenv("ORT_INNER_MIN")) c->inner_min = std::atoi(e2);
     if (const char* e2 = std::getenv("ORT_FUSE")) c->fuse = std::atoi(e2);
+    if (const char* e2 = std::getenv("ORT_BVH8")) c->bvh8 = std::atoi(e2);
     if (const char* e2 = std::getenv("ORT_EXP_CTAS")) {
         c->exp_ctas = std::atoi(e2);
         if (c->exp_ctas > 0) {
@@ -605,6 +616,10 @@ int ort_create(ort_ctx** out, const ort_device_cfg* cfg) {
     ORT_OCC(0, 0, true, false, false) ORT_OCC(0, 1, false, true, false) ORT_OCC(0, 2, true, true, false)
     ORT_OCC(1, 0, true, false, true) ORT_OCC(1, 1, false, true, true) ORT_OCC(1, 2, true, true, true)
 #undef ORT_OCC
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace8<true>, TRACE_THREADS, 0);
+    c->trace8_grid[0] = c->sm_count * std::max(occ, 1);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace8<false>, TRACE_THREADS, 0);
+    c->trace8_grid[1] = c->sm_count * std::max(occ, 1);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shade, 256, 0);
     c->shade_grid = c->sm_count * std::max(occ, 1);
     *out = c;
@@ -671,10 +686,17 @@ int ort_upload_scene(ort_ctx* ctx, const ort_scene* sc) {
     // builds and uploads the per-triangle records, which do not depend on it.
     const char* why_scene = nullptr;
     const char* why_light = nullptr;
-    bool ok_scene = false, ok_light = false;
+    bool ok_scene = false, ok_light = false, ok8 = false;
     std::thread wide_thread([&] {
         ok_scene = build_wide_bvh(sc->bvh, sc->n_bvh_nodes, sc->n_triangles, &ctx->wide, &why_scene);
         ok_light = build_wide_bvh(sc->light_bvh, sc->n_light_bvh_nodes, sc->n_light_triangles, &ctx->lwide, &why_light);
+        ok8 = false;
+        if (ctx->bvh8 && ok_scene && ok_light) {
+            const char* why8 = nullptr; // e.g. leaves larger than the reference's 4: stay on the 4-wide tree
+            ok8 = build_wide8_bvh(sc->bvh, sc->n_bvh_nodes, sc->n_triangles, &ctx->wide8, &why8) &&
+                  build_wide8_bvh(sc->light_bvh, sc->n_light_bvh_nodes, sc->n_light_triangles, &ctx->lwide8, &why8) &&
+                  ctx->wide8.depth <= MAX_STACK && ctx->lwide8.depth <= MAX_STACK;
+        }
     });
     struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{wide_thread};
 
@@ -845,6 +867,44 @@ int ort_upload_scene(ort_ctx* ctx, const ort_scene* sc) {
         }
         sd.nodes = (const float4*)d;
         sd.light_root = (int32_t)ns;
+    }
+    ctx->use8 = ok8 && !ctx->quant;
+    if (ctx->use8) {
+        // 8-wide tree: nodes (scene, then light with rebased references) and traversal-order triangle records
+        const size_t ns8 = ctx->wide8.nodes.size(), nl8 = ctx->lwide8.nodes.size();
+        if (scene_buffer(ctx, ort_ctx::SB_NODES8, (ns8 + nl8) * sizeof(Wide8Node), &d)) return 1;
+        sd.nodes8 = (const float4*)d;
+        sd.light_root8 = (int32_t)ns8;
+        if (staged_upload(ctx, d, ns8, sizeof(Wide8Node), 4096,
+                          [&](size_t f, size_t c, void* o) { std::memcpy(o, ctx->wide8.nodes.data() + f, c * sizeof(Wide8Node)); }))
+            return 1;
+        if (staged_upload(ctx, (char*)d + ns8 * sizeof(Wide8Node), nl8, sizeof(Wide8Node), 4096, [&](size_t f, size_t c, void* o) {
+                for (size_t i = 0; i < c; i++) {
+                    Wide8Node w = ctx->lwide8.nodes[f + i];
+                    w.child_base += (uint32_t)ns8;
+                    w.tri_base += (uint32_t)nt;
+                    ((Wide8Node*)o)[i] = w;
+                }
+            }))
+            return 1;
+        if (scene_buffer(ctx, ort_ctx::SB_TRIS8, (nt + nlt) * sizeof(TriIsect), &d)) return 1;
+        sd.tris8 = (const float4*)d;
+        auto fill8 = [&](const ort_triangle* tris, const std::vector<uint32_t>& order, uint32_t id_base) {
+            return [=, &order](size_t f, size_t c, void* o) {
+                TriIsect* rec = (TriIsect*)o;
+                for (size_t i = 0; i < c; i++) {
+                    const uint32_t ref = order[f + i];
+                    make_isect_records(tris + ref, 1, rec + i);
+                    const uint32_t id = id_base + ref;
+                    std::memcpy(&rec[i].pad[0], &id, 4);
+                }
+            };
+        };
+        if (ctx->wide8.tri_order.size() != nt || ctx->lwide8.tri_order.size() != nlt) return fail(ctx, "8-wide BVH does not cover every triangle exactly once");
+        if (staged_upload(ctx, d, nt, sizeof(TriIsect), 4096, fill8(sc->triangles, ctx->wide8.tri_order, 0u))) return 1;
+        if (staged_upload(ctx, (char*)d + nt * sizeof(TriIsect), nlt, sizeof(TriIsect), 4096,
+                          fill8(sc->light_triangles, ctx->lwide8.tri_order, (uint32_t)nt)))
+            return 1;
     }
     sd.n_lights = (int32_t)sc->n_light_triangles;
     std::memcpy(sd.pad_scale, ctx->wide.max_abs, 12);

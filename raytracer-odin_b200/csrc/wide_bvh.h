@@ -81,6 +81,33 @@ struct alignas(16) QuantNode {
 };
 static_assert(sizeof(QuantNode) == 64, "QuantNode must be half a cache line");
 
+// 8-wide node, 256 bytes.  Child boxes in SoA form [axis][lo|hi][8 slots] (192 bytes: the near / far
+// vector of an axis is one 32-byte load picked by a per-ray offset), then a header and the per-slot
+// triangle masks.  Inner children are stored contiguously in slot order: child index =
+// child_base + popcount(imask & ((1 << slot) - 1)).  The triangles of all leaf children of a node are
+// contiguous in the TRAVERSAL-ORDER triangle array (tris8) starting at tri_base, in slot order and, inside a
+// leaf, in the reference's order; trimask[slot] has one bit per triangle of that leaf (0 for inner / empty
+// slots), so a node references at most 32 triangles (8 leaves of <= 4, raytracer.odin:230).  Slots are
+// assigned so that slot bit a (x: 1, y: 2, z: 4) is set for children on the positive side of the node's
+// centre along axis a: visiting the hit slots in ascending order of (slot ^ octant of the ray direction)
+// is a near-to-far order without any per-visit sorting (Ylitie et al. 2017).
+struct alignas(32) Wide8Node {
+    float bounds[3][2][8];
+    uint32_t child_base, tri_base, imask, pad0;
+    uint32_t pad1[4];
+    uint32_t trimask[8];
+};
+static_assert(sizeof(Wide8Node) == 256, "Wide8Node must be two cache lines");
+
+struct Wide8BVH {
+    std::vector<Wide8Node> nodes;     // root = 0
+    std::vector<uint32_t> tri_order;  // traversal-order position -> reference triangle index
+    int depth = 0;                    // = worst-case stack occupancy (one entry per level)
+};
+// Re-emit the binary reference BVH as an 8-wide BVH.  Returns false with *err set when the input is
+// malformed or a node would reference more than 32 triangles (leaves larger than the reference's 4).
+bool build_wide8_bvh(const ort_bvh_node* bvh, int64_t n_nodes, int64_t n_tris, Wide8BVH* out, const char** err);
+
 struct WideBVH {
     std::vector<WideNode> nodes; // root = 0
     int depth = 0;               // wide levels, root = 1
