@@ -288,6 +288,8 @@ int make_texture(ort_ctx* ctx, const ort_texture& t, bool srgb, cudaTextureObjec
 }
 
 int ensure_paths(ort_ctx* ctx, int64_t need, int pipes = 1) {
+    if (const char* lim = std::getenv("ORT_TEST_MAX_PATH_BYTES")) // test hook: pretend the GPU has only this much room
+        if ((double)need * (16 * 10 + 12) * pipes > std::atof(lim)) return fail(ctx, "cudaMalloc: out of memory (simulated)");
     for (int i = 0; i < pipes; i++) {
         auto& P = ctx->ps[i];
         if (P.capacity >= need) continue;
@@ -468,13 +470,23 @@ int render_impl(ort_ctx* ctx, uint32_t w, uint32_t h, int32_t depth, uint64_t fi
     if ((uint64_t)cap < npix) cap = (int64_t)npix;
     uint64_t per_wave = std::max<uint64_t>(1, (uint64_t)cap / npix);
     if (per_wave > n_samples) per_wave = std::max<uint64_t>(n_samples, 1);
-    // two wave pipelines on two streams: the tail of every persistent kernel of one wave (a few
-    // warps finishing their last rays) is filled by the other wave's kernels
-    const uint64_t n_waves = (n_samples + per_wave - 1) / per_wave;
-    int pipes = std::max(1, std::min(ctx->overlap, MAX_PIPES));
-    if (ctx->profiling || interrupt || depth == 0) pipes = 1;
-    if ((uint64_t)pipes > n_waves) pipes = (int)n_waves;
-    if (ensure_paths(ctx, (int64_t)(per_wave * npix), pipes)) return 1;
+    // several wave pipelines on separate streams: the tail of every persistent kernel of one wave (a
+    // few warps finishing their last rays) is filled by the other waves' kernels
+    int pipes = 1;
+    for (;;) {
+        const uint64_t n_waves = (n_samples + per_wave - 1) / per_wave;
+        pipes = std::max(1, std::min(ctx->overlap, MAX_PIPES));
+        if (ctx->profiling || interrupt || depth == 0) pipes = 1;
+        if ((uint64_t)pipes > n_waves) pipes = (int)n_waves;
+        if (ensure_paths(ctx, (int64_t)(per_wave * npix), pipes) == 0) break;
+        // not enough free HBM for this many paths in flight (other contexts / processes on the GPU):
+        // fall back to smaller waves, then to fewer pipelines, before giving up
+        cudaGetLastError();
+        free_paths(ctx);
+        if (per_wave > 1) per_wave = (per_wave + 1) / 2;
+        else if (ctx->overlap > 1) ctx->overlap = 1;
+        else return 1; // ctx->err holds the cudaMalloc message
+    }
     if (ensure_counters(ctx, depth, pipes)) return 1;
     RenderParams p;
     fill_params(ctx, w, h, depth, &p);

@@ -167,3 +167,27 @@ def test_cpp_cli_equals_python_cli(scene_dir, tmp_path):
     assert r.returncode == 0 and "Performance Summary" in r.stdout, r.stderr
     t2, _ = api.load_checkpoint(ck_c, 48, 32)
     assert np.all(t2["count"] == 4)
+
+
+@pytest.mark.gpu
+def test_cpp_cli_continious_until_sigint(scene_dir, tmp_path):
+    """--continious (main.odin:207): render 16-sample chunks until SIGINT, then write the image and the
+    checkpoint; the sample count is whatever finished, every pixel got the same number of samples."""
+    import signal
+    import time
+
+    hostlib.load()
+    p = scenegen.cornell(os.path.join(scene_dir, "cpp_cli_cont.gltf"))
+    out, ck = str(tmp_path / "cont.ppm"), str(tmp_path / "cont.ckpt")
+    proc = subprocess.Popen([hostlib.CLI_PATH, p, out, "--width", "64", "--height", "48", "--ray-depth", "4",
+                             "--continious", "--checkpoint", ck], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    time.sleep(6.0)
+    proc.send_signal(signal.SIGINT)
+    stdout, stderr = proc.communicate(timeout=60)
+    assert proc.returncode == 0, stderr
+    assert "Rendered" in stdout and "samples in" in stdout
+    px, nxt = api.load_checkpoint(ck, 64, 48)
+    assert nxt > 0 and nxt % 16 == 0
+    # an interrupted last chunk may be partial, but whole waves only: counts are uniform over the image
+    assert px["count"].min() == px["count"].max() and 0 < px["count"][0] <= nxt
+    assert os.path.getsize(out) == len(b"P6\n64 48\n255\n") + 64 * 48 * 3

@@ -466,3 +466,24 @@ def test_wide8_traversal_matches_default(scenes, monkeypatch):
         np.testing.assert_allclose(l4, l8, rtol=2e-5, atol=1e-7)
         rmse, lum = api.rel_rmse(api.mean_image(px8, 48, 32), api.mean_image(px4, 48, 32))
         assert rmse < 1e-3 and abs(lum - 1) < 1e-3, (name, rmse, lum)
+
+
+@pytest.mark.gpu
+def test_falls_back_to_smaller_waves_when_memory_is_short(scenes, monkeypatch):
+    """When the path buffers of the default wave size do not fit (other contexts on the GPU), the render
+    uses smaller waves / fewer pipelines instead of failing, with identical results (the counter-based
+    streams make the wave split invisible)."""
+    from raytracer_odin_b200 import api
+
+    s = scenes("cornell")
+    with api.Renderer(seed=9).upload_scene(s) as r:
+        ref = r.render(64, 64, 4, 32)
+    monkeypatch.setenv("ORT_TEST_MAX_PATH_BYTES", str(64 * 64 * 172 * 5))  # room for 5 samples in flight
+    with api.Renderer(seed=9).upload_scene(s) as r:
+        small = r.render(64, 64, 4, 32)
+    monkeypatch.setenv("ORT_TEST_MAX_PATH_BYTES", "1000")  # not even one sample per pixel fits
+    with api.Renderer(seed=9).upload_scene(s) as r:
+        with pytest.raises(api.OrtError, match="out of memory"):
+            r.render(64, 64, 4, 32)
+    assert np.array_equal(ref["count"], small["count"])
+    np.testing.assert_allclose(ref["total"], small["total"], rtol=1e-5, atol=1e-6)
