@@ -365,6 +365,15 @@ def main():
                 "note": "C1-C4 traversal working sets sit in the 126 MB L2 (SURVEY §8d), so achieved "
                         "algorithmic GB/s may exceed the HBM copy peak; ncu dram bytes are in profiles/"}
         roof["frac"] = (roof["achieved"] / peak) if roof["achieved"] else None
+        # C1-C4 traversal working sets are L2 resident, so the same algorithmic GB/s is also
+        # held against the box's L2 read bandwidth, measured here with the library's streaming-read probe
+        # on a working set of the scene's size (nodes + traversal triangles, at least 32 MB to stay out of L1)
+        ws = ps["wide_nodes"] * 128 + ps["light_wide_nodes"] * 128 + (len(scene.triangles) + len(scene.light_triangles)) * 64
+        probe = max(ws, 32 << 20)
+        l2_gbs = r.bench_read_bw(probe, 20 if probe <= (256 << 20) else 5)
+        roof["l2"] = {"working_set_bytes": int(ws), "probe_bytes": int(probe), "peak": l2_gbs, "unit": "GB/s",
+                      "peak_source": "measured in this run: ort_bench_read_bw, 256-bit read-only loads from all SMs",
+                      "frac": (roof["achieved"] / l2_gbs) if roof["achieved"] else None}
 
     if rank == 0:
         line = {

@@ -218,6 +218,12 @@ int  ort_tonemap_rgb8(ort_ctx* ctx, uint32_t w, uint32_t h, const float* d_accum
  * one launch in milliseconds (CUDA events).  Used by tools/trace_bench.py to compare kernel variants. */
 int  ort_bench_trace(ort_ctx* ctx, const ort_ray* rays, int64_t n, int32_t mode, int32_t iters, double* ms_per_launch);
 
+/* Diagnostic: streaming-read bandwidth of a working set of `bytes` (256-bit read-only loads from every
+ * SM, `iters` passes after one warm-up pass), in GB/s.  With a working set between the total L1 size
+ * and the L2 size this is the box's L2 read bandwidth — the peak SURVEY §8(d) asks the build to measure
+ * for the L2-resident scenes (C1-C4); with a multi-GB working set it is the HBM read bandwidth. */
+int  ort_bench_read_bw(ort_ctx* ctx, int64_t bytes, int32_t iters, double* gb_per_s);
+
 int  ort_get_stats(ort_ctx* ctx, ort_stats* out);
 int  ort_reset_stats(ort_ctx* ctx);
 /* When on, render calls time each kernel class with CUDA events (serialises the pipeline). */

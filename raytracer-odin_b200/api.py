@@ -152,6 +152,12 @@ class Renderer:
         self._check(self.lib.ort_bench_trace(self._ctx, cabi.ptr(rays), len(rays), mode, iters, C.byref(ms)))
         return ms.value
 
+    def bench_read_bw(self, nbytes: int, iters: int = 20) -> float:
+        """Streaming-read bandwidth (GB/s) of a working set of `nbytes` (L2 peak for 32-96 MB, HBM for GBs)."""
+        g = C.c_double()
+        self._check(self.lib.ort_bench_read_bw(self._ctx, nbytes, iters, C.byref(g)))
+        return g.value
+
     # -- stats ---------------------------------------------------------------------------------
     def stats(self) -> dict:
         s = cabi.OrtStats()

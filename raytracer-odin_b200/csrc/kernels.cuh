@@ -710,6 +710,19 @@ __global__ void k_scale(float* __restrict__ x, const uint32_t n, const float inv
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) x[i] = x[i] / inv;
 }
 
+// streaming read of n32 32-byte units, `iters` times (bandwidth probe: L2 when the buffer fits it)
+__global__ void __launch_bounds__(256) k_read_bw(const float4* __restrict__ p, const size_t n32, const int iters,
+                                                 float* __restrict__ sink) {
+    float acc = 0.0f;
+    const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    for (int it = 0; it < iters; it++)
+        for (size_t i = i0; i < n32; i += stride) {
+            const F8 v = ldg8(p + 2 * i);
+            acc += v.lo.x + v.hi.w;
+        }
+    if (acc == 123.456f) *sink = acc; // never true for the zero-filled buffer: keeps the loads alive
+}
+
 // planar accumulators (+ optional first/last planes) -> Sample_Stats AoS (13 words / pixel)
 __global__ void k_pack_stats(const float* __restrict__ accum, const float* __restrict__ first,
                              const float* __restrict__ last, const uint32_t npix, uint32_t* __restrict__ out13) {

@@ -1044,6 +1044,28 @@ int ort_bench_trace(ort_ctx* ctx, const ort_ray* rays, int64_t n, int32_t mode, 
     return 0;
 }
 
+int ort_bench_read_bw(ort_ctx* ctx, int64_t bytes, int32_t iters, double* gb_per_s) {
+    if (!ctx) return 1;
+    if (bytes < 32 || iters < 1 || !gb_per_s) return fail(ctx, "ort_bench_read_bw: bad arguments");
+    Bind b(ctx->device);
+    const size_t n32 = (size_t)bytes / 32;
+    if (ensure_scratch(ctx, n32 * 32 + 256)) return 1;
+    CK(cudaMemsetAsync(ctx->scratch, 0, n32 * 32 + 256, ctx->stream));
+    const int grid = ctx->sm_count * 8;
+    float* sink = ctx->scratch + n32 * 8;
+    k_read_bw<<<grid, 256, 0, ctx->stream>>>((const float4*)ctx->scratch, n32, 1, sink); // warm-up: fills L2
+    CK(cudaEventRecord(ctx->evp0, ctx->stream));
+    k_read_bw<<<grid, 256, 0, ctx->stream>>>((const float4*)ctx->scratch, n32, iters, sink);
+    CK(cudaEventRecord(ctx->evp1, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    ctx->launches += 2;
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ctx->evp0, ctx->evp1));
+    *gb_per_s = (double)n32 * 32.0 * iters / ((double)ms * 1e-3) / 1e9;
+    return 0;
+}
+
 int ort_light_pdf(ort_ctx* ctx, const ort_ray* rays, int64_t n, float* out) {
     if (!ctx) return 1;
     if (!ctx->has_scene) return fail(ctx, "ort_upload_scene has not been called");
