@@ -260,25 +260,28 @@ def main():
         dist.barrier()
     r.reset_stats()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     with ClockSampler(local) as clocks:
         torch.cuda.synchronize()
         e0.record(stream)
         for i in range(args.steps):
             step(args.warmup + i)
+            marks[i].record(stream)  # per-step times: best / median / worst like the reference's summary
         e1.record(stream)
         torch.cuda.synchronize()
+    step_ms = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
     if world > 1:
         dist.barrier()
     ms = e0.elapsed_time(e1)
     st = r.stats()
     t = torch.tensor([ms, float(st["rays_closest"]), float(st["rays_traced"]), float(st["paths"]),
-                      float(st["kernel_launches"])], device="cuda", dtype=torch.float64)
+                      float(st["kernel_launches"]), float(st["rays_light_pdf"])], device="cuda", dtype=torch.float64)
     if world > 1:
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         ms = float(tmax[0])
-    rays, traced, paths, launches = (float(x) for x in t[1:])
+    rays, traced, paths, launches, light_rays = (float(x) for x in t[1:])
     value = rays / (ms * 1e-3) / 1e6
 
     # ---- e2e: public host call, HOST buffers, scene H2D + Sample_Stats D2H inside the timed region
@@ -365,6 +368,13 @@ def main():
                 "note": "C1-C4 traversal working sets sit in the 126 MB L2 (SURVEY §8d), so achieved "
                         "algorithmic GB/s may exceed the HBM copy peak; ncu dram bytes are in profiles/"}
         roof["frac"] = (roof["achieved"] / peak) if roof["achieved"] else None
+        # second fraction: compulsory HBM traffic of the wavefront design per traced ray and bounce —
+        # k_trace reads the ray (32 B) and writes the hit (16 B); k_shade reads ray, hit, pending payload and
+        # light sum (84 B) and writes the next ray + payload + light-queue entry (68 B) — against the HBM peak
+        state_bpr = 32 + 16 + 84 + 68
+        roof["state_traffic"] = {"bytes_per_ray_bounce": state_bpr, "unit": "GB/s",
+                                 "achieved": state_bpr * traced / world / (ms * 1e-3) / 1e9,  # per GPU
+                                 "frac": state_bpr * traced / world / (ms * 1e-3) / 1e9 / peak}
         # C1-C4 traversal working sets are L2 resident, so the same algorithmic GB/s is also
         # held against the box's L2 read bandwidth, measured here with the library's streaming-read probe
         # on a working set of the scene's size (nodes + traversal triangles, at least 32 MB to stay out of L1)
@@ -382,7 +392,8 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args.config, cfg, scene, spp),
             "samples_per_s": paths / (ms * 1e-3), "frames_1080p_spp_per_s": paths / (ms * 1e-3) / 2073600.0,
-            "rays_traced_per_s": traced / (ms * 1e-3),
+            "rays_traced_per_s": traced / (ms * 1e-3), "light_pdf_rays_per_s": light_rays / (ms * 1e-3),
+            "step_ms": {"best": min(step_ms), "median": float(np.median(step_ms)), "worst": max(step_ms)},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(npix * 52), "steps": e2e_steps,
                     "upload_ms": [round(a, 2) for a, _ in e2e_parts[1:]],
