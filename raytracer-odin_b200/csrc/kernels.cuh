@@ -75,6 +75,7 @@ struct RenderParams {
     uint32_t n_batch_samples;
     uint64_t sample_base;
     uint64_t seed;
+    int32_t tiled; // primary rays enter the queue in 8x4 pixel tiles (render) or in pixel order (probes)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -182,15 +183,39 @@ __device__ __forceinline__ f3 primary_dir(const RenderParams& p, uint32_t px, ui
     return mk3(divr(v[0], len), divr(v[1], len), divr(v[2], len));
 }
 
+// Queue position -> pixel.  The path SLOT of a ray stays s_local * npix + (py * w + px) (RNG keys, state
+// and accumulation are indexed by it), but the ORDER in which primary rays enter the queue follows 8x4
+// pixel tiles, so the 32 rays a traversal warp fetches together cover a compact 8x4 footprint instead
+// of a 32x1 strip (more shared nodes per request, fewer distinct sectors).  Pixels outside the region
+// covered by whole tiles (w % 8 columns on the right, h % 4 rows at the bottom) follow in row order.
+__device__ __forceinline__ uint32_t tiled_pixel(uint32_t q, uint32_t w, uint32_t h) {
+    const uint32_t w8 = w & ~7u, h4 = h & ~3u, area = w8 * h4;
+    if (q < area) {
+        const uint32_t tile = q >> 5, in = q & 31u, tiles_x = w8 >> 3;
+        const uint32_t ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        return (ty * 4u + (in >> 3)) * w + tx * 8u + (in & 7u);
+    }
+    uint32_t r = q - area;
+    const uint32_t right = (w - w8) * h; // the right strip, all rows
+    if (r < right) {
+        const uint32_t y = r / (w - w8);
+        return y * w + w8 + (r - y * (w - w8));
+    }
+    r -= right; // the bottom strip under the tiled region
+    const uint32_t y = r / w8;
+    return (h4 + y) * w + (r - y * w8);
+}
+
 __global__ void k_raygen(const RenderParams p, float4* __restrict__ qo, float4* __restrict__ qd,
                          uint32_t* __restrict__ count0) {
     const uint32_t n = p.n_batch_samples * p.npix;
     if (blockIdx.x == 0 && threadIdx.x == 0) *count0 = n;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t s_local = i / p.npix, pix = i - s_local * p.npix;
+        const uint32_t s_local = i / p.npix;
+        const uint32_t pix = p.tiled ? tiled_pixel(i - s_local * p.npix, p.w, p.h) : i - s_local * p.npix;
         const uint32_t py = pix / p.w, px = pix - py * p.w;
         const f3 d = primary_dir(p, px, py, pix, p.sample_base + s_local);
-        qo[i] = make_float4(p.cam_pos[0], p.cam_pos[1], p.cam_pos[2], __uint_as_float(i));
+        qo[i] = make_float4(p.cam_pos[0], p.cam_pos[1], p.cam_pos[2], __uint_as_float(s_local * p.npix + pix));
         qd[i] = make_float4(d.x, d.y, d.z, 0.0f);
     }
 }

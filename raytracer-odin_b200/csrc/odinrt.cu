@@ -89,6 +89,7 @@ struct ort_ctx {
     int trace_grid[2][3] = {{0, 0, 0}, {0, 0, 0}}; // [node encoding][mode] persistent grid sizes
     int shade_grid = 0;
     bool quant = false; // scene uses QuantNode
+    int tiled = 1;    // env ORT_TILED=0: primary rays in pixel order instead of 8x4 tiles
     int exp_ctas = 0; // env ORT_EXP_CTAS=n: occupancy experiment, at most n traversal CTAs per SM
     int fuse = 0; // env ORT_FUSE=1: trace closest hit + light sum in one fused pass
     int bin_octants = 1;     // env ORT_BIN=0: plain per-warp queue compaction (no direction-octant binning)
@@ -398,6 +399,7 @@ void fill_params(ort_ctx* ctx, uint32_t w, uint32_t h, int32_t depth, RenderPara
     p->seed = ctx->seed;
     p->n_batch_samples = 1;
     p->sample_base = 0;
+    p->tiled = 0;
 }
 
 // One wave: n_batch_samples samples of every pixel, all bounces, then accumulation.  `wait_for` is
@@ -490,6 +492,7 @@ int render_impl(ort_ctx* ctx, uint32_t w, uint32_t h, int32_t depth, uint64_t fi
     if (ensure_counters(ctx, depth, pipes)) return 1;
     RenderParams p;
     fill_params(ctx, w, h, depth, &p);
+    p.tiled = ctx->tiled;
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     if (pipes > 1) {
         CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
@@ -590,6 +593,7 @@ int ort_create(ort_ctx** out, const ort_device_cfg* cfg) {
     if (const char* e2 = std::getenv("ORT_INNER_MIN")) c->inner_min = std::atoi(e2);
     if (const char* e2 = std::getenv("ORT_FUSE")) c->fuse = std::atoi(e2);
     if (const char* e2 = std::getenv("ORT_BVH8")) c->bvh8 = std::atoi(e2);
+    if (const char* e2 = std::getenv("ORT_TILED")) c->tiled = std::atoi(e2);
     if (const char* e2 = std::getenv("ORT_EXP_CTAS")) {
         c->exp_ctas = std::atoi(e2);
         if (c->exp_ctas > 0) {
