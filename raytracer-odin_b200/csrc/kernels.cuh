@@ -76,6 +76,7 @@ struct RenderParams {
     uint64_t sample_base;
     uint64_t seed;
     int32_t tiled; // primary rays enter the queue in 8x4 pixel tiles (render) or in pixel order (probes)
+    int32_t tile_w, tile_h, tile_s; // tiled >= 2: pixels x samples per warp (experiment)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -211,8 +212,27 @@ __global__ void k_raygen(const RenderParams p, float4* __restrict__ qo, float4* 
     const uint32_t n = p.n_batch_samples * p.npix;
     if (blockIdx.x == 0 && threadIdx.x == 0) *count0 = n;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t s_local = i / p.npix;
-        const uint32_t pix = p.tiled ? tiled_pixel(i - s_local * p.npix, p.w, p.h) : i - s_local * p.npix;
+        uint32_t s_local, pix;
+        if (p.tiled >= 2 && (p.w % (uint32_t)p.tile_w) == 0u && (p.h % (uint32_t)p.tile_h) == 0u &&
+            (p.n_batch_samples % (uint32_t)p.tile_s) == 0u) {
+            // a warp = tile_w x tile_h pixels x tile_s samples (product 32; default 2 x 2 x 8): the 32 rays
+            // differ only by sub-pixel jitter and one pixel step, and the sample groups of one pixel tile
+            // follow each other in the queue.  Measured against 8x4x1: k_trace -7 % (profiles/r1_sensitivity.md)
+            const uint32_t tw = (uint32_t)p.tile_w, th = (uint32_t)p.tile_h, ts = (uint32_t)p.tile_s;
+            const uint32_t tp = tw * th;
+            const uint32_t block = i >> 5, in = i & 31u;
+            const uint32_t sin = in / tp, pin = in - sin * tp;
+            const uint32_t sgroups = p.n_batch_samples / ts;
+            const uint32_t pg = block / sgroups, sg = block - pg * sgroups;
+            const uint32_t tiles_x = p.w / tw;
+            const uint32_t ty = pg / tiles_x, tx = pg - ty * tiles_x;
+            const uint32_t iy = pin / tw, ix = pin - iy * tw;
+            s_local = sg * ts + sin;
+            pix = (ty * th + iy) * p.w + tx * tw + ix;
+        } else {
+            s_local = i / p.npix;
+            pix = p.tiled ? tiled_pixel(i - s_local * p.npix, p.w, p.h) : i - s_local * p.npix;
+        }
         const uint32_t py = pix / p.w, px = pix - py * p.w;
         const f3 d = primary_dir(p, px, py, pix, p.sample_base + s_local);
         qo[i] = make_float4(p.cam_pos[0], p.cam_pos[1], p.cam_pos[2], __uint_as_float(s_local * p.npix + pix));

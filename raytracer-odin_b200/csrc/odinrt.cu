@@ -89,7 +89,7 @@ struct ort_ctx {
     int trace_grid[2][3] = {{0, 0, 0}, {0, 0, 0}}; // [node encoding][mode] persistent grid sizes
     int shade_grid = 0;
     bool quant = false; // scene uses QuantNode
-    int tiled = 1;    // env ORT_TILED=0: primary rays in pixel order instead of 8x4 tiles
+    int tiled = 2;    // env ORT_TILED: 0 = primary rays in pixel order, 1 = 8x4 pixel tiles, 2 = 2x2 pixels x 8 samples per warp (ORT_TILE=WxHxS)
     int exp_ctas = 0; // env ORT_EXP_CTAS=n: occupancy experiment, at most n traversal CTAs per SM
     int fuse = 0; // env ORT_FUSE=1: trace closest hit + light sum in one fused pass
     int bin_octants = 1;     // env ORT_BIN=0: plain per-warp queue compaction (no direction-octant binning)
@@ -400,6 +400,7 @@ void fill_params(ort_ctx* ctx, uint32_t w, uint32_t h, int32_t depth, RenderPara
     p->n_batch_samples = 1;
     p->sample_base = 0;
     p->tiled = 0;
+    p->tile_w = 2; p->tile_h = 2; p->tile_s = 8;
 }
 
 // One wave: n_batch_samples samples of every pixel, all bounces, then accumulation.  `wait_for` is
@@ -493,6 +494,7 @@ int render_impl(ort_ctx* ctx, uint32_t w, uint32_t h, int32_t depth, uint64_t fi
     RenderParams p;
     fill_params(ctx, w, h, depth, &p);
     p.tiled = ctx->tiled;
+    if (const char* e2 = std::getenv("ORT_TILE")) { int a_ = 2, b_ = 2, c_ = 8; if (std::sscanf(e2, "%dx%dx%d", &a_, &b_, &c_) == 3 && a_ * b_ * c_ == 32) { p.tile_w = a_; p.tile_h = b_; p.tile_s = c_; } }
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     if (pipes > 1) {
         CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
