@@ -29,7 +29,21 @@ def worker(config):
     D = s + N; D /= np.linalg.norm(D, axis=1, keepdims=True)
     b1 = np.zeros(len(P), cabi.RAY_DTYPE); b1["o"] = P.astype(np.float32); b1["d"] = D.astype(np.float32)
     out = {"config": config, "lib": os.environ.get("ORT_LIB", "default"), "n_primary": len(rays), "n_bounce1": len(b1)}
-    for name, rs in (("primary", rays), ("bounce1", b1), ("bounce1_shuffled", b1[rng.permutation(len(b1))])):
+    def binned(rs, seg, nbits):
+        """reorder inside consecutive segments of `seg` rays by a direction-bin key (stable)"""
+        d = rs["d"]
+        key = (d[:, 0] < 0) * 1 + (d[:, 1] < 0) * 2 + (d[:, 2] < 0) * 4
+        if nbits > 3:
+            ad = np.abs(d)
+            key = key * 4 + (ad[:, 0] > ad[:, 1]) * 2 + (ad[:, 2] > np.maximum(ad[:, 0], ad[:, 1])) * 1
+        segid = np.arange(len(rs)) // seg
+        order = np.lexsort((key, segid))
+        return rs[order]
+    sets = [("primary", rays), ("bounce1", b1), ("bounce1_shuffled", b1[rng.permutation(len(b1))])]
+    if os.environ.get("ORT_BENCH_ORDERS"):
+        sets += [("b1_oct256", binned(b1, 256, 3)), ("b1_oct4096", binned(b1, 4096, 3)), ("b1_dir32_1024", binned(b1, 1024, 5)),
+                 ("b1_dir32_4096", binned(b1, 4096, 5)), ("b1_dir32_65536", binned(b1, 65536, 5)), ("b1_dir32_global", binned(b1, 1 << 30, 5))]
+    for name, rs in sets:
         ms = r.bench_trace(rs, 0, 10)
         out[name + "_ms"] = round(ms, 3); out[name + "_Grays/s"] = round(len(rs) / ms / 1e6, 3)
     if len(scene.light_triangles):
