@@ -253,6 +253,14 @@ int  ort_multi_get_stats(ort_multi* m, ort_stats* out); /* counters summed, time
  * (or a negative error code). */
 int64_t ort_bvh_build(ort_triangle* tris, int64_t n, ort_bvh_node* nodes_out, int64_t cap);
 
+/* Host-side helper: the 4-wide, 128-byte-node re-emission of a binary reference BVH that
+ * ort_upload_scene performs internally (breadth-first, root = node 0; layout in csrc/wide_bvh.h), on
+ * `threads` host threads (0 = all cores; the output does not depend on the count).  For tools and
+ * tests; returns the number of wide nodes (written to nodes_out when it has room for them), -1 on
+ * malformed input, -2 when cap is too small. */
+int64_t ort_wide_bvh_emit(const ort_bvh_node* bvh, int64_t n_nodes, int64_t n_tris, int32_t threads,
+                          void* nodes_out, int64_t cap, int32_t* depth, int32_t* max_stack);
+
 /* The same builder on the GPU: identical splits, permutation and post-order
  * node array as ort_bvh_build / the reference, every tree level processed at once (device-wide
  * stable radix sorts on (segment, lo[axis]) keys, segmented box scans, per-segment arg-min).

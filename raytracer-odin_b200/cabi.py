@@ -108,6 +108,8 @@ ABI = {
     "ort_light_pdf": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "ort_tonemap_rgb8": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
     "ort_bench_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_double)]),
+    "ort_wide_bvh_emit": (C.c_int64, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int64,
+                                      C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "ort_bench_read_bw": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.POINTER(C.c_double)]),
     "ort_get_stats": (C.c_int, [C.c_void_p, C.POINTER(OrtStats)]),
     "ort_reset_stats": (C.c_int, [C.c_void_p]),

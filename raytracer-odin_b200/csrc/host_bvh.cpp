@@ -12,6 +12,7 @@
 #include "wide_bvh.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <future>
@@ -172,21 +173,51 @@ struct Build {
 
 } // namespace
 
-bool build_wide_bvh(const ort_bvh_node* bvh, int64_t n_nodes, int64_t n_tris, WideBVH* out, const char** err) {
+namespace {
+
+// fn(first, count) over [0, n) on up to `threads` host threads (inline for small ranges)
+template <typename F>
+void par_for(size_t n, int threads, size_t min_per_thread, F fn) {
+    size_t nt = std::min<size_t>((size_t)std::max(threads, 1), n / std::max<size_t>(min_per_thread, 1));
+    if (nt <= 1) { if (n) fn((size_t)0, n); return; }
+    std::vector<std::thread> pool;
+    const size_t per = (n + nt - 1) / nt;
+    for (size_t t = 1; t < nt; t++) {
+        const size_t a = t * per, b = std::min(n, a + per);
+        if (a < b) pool.emplace_back([=] { fn(a, b - a); });
+    }
+    fn((size_t)0, std::min(n, per));
+    for (auto& th : pool) th.join();
+}
+
+} // namespace
+
+// Level-synchronous and parallel: the nodes of one wide level are independent once their output
+// indices are known, and those follow from an exclusive scan of the per-node inner-child counts in
+// queue order — exactly the indices the serial breadth-first emission hands out, so the result does
+// not depend on the thread count (tests/test_host.py compares 1 and 16 threads).
+bool build_wide_bvh(const ort_bvh_node* bvh, int64_t n_nodes, int64_t n_tris, WideBVH* out, const char** err, int threads) {
     out->nodes.clear();
     out->depth = 0;
     out->max_stack = 0;
     if (n_nodes <= 0) { *err = "empty BVH node array"; return false; }
-    for (int64_t i = 0; i < n_nodes; i++) {
-        const ort_bvh_node& nd = bvh[i];
-        if (nd.kind == 0) {
-            if (nd.a < 0 || nd.b < 0 || nd.b > 7 || nd.a + nd.b > n_tris || nd.a >= (1 << 28)) {
-                *err = "BVH leaf out of range (first/count)"; return false;
+    if (threads <= 0) threads = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    {
+        std::atomic<int> bad{0};
+        par_for((size_t)n_nodes, threads, 1 << 16, [&](size_t f, size_t c) {
+            for (size_t i = f; i < f + c; i++) {
+                const ort_bvh_node& nd = bvh[i];
+                if (nd.kind == 0) {
+                    if (nd.a < 0 || nd.b < 0 || nd.b > 7 || nd.a + nd.b > n_tris || nd.a >= (1 << 28)) bad.store(1);
+                } else if (nd.kind == 1) {
+                    // post-order: children precede their parent
+                    if (nd.a < 0 || nd.b < 0 || nd.a >= (int64_t)i || nd.b >= (int64_t)i) bad.store(2);
+                } else bad.store(3);
             }
-        } else if (nd.kind == 1) {
-            // post-order: children precede their parent
-            if (nd.a < 0 || nd.b < 0 || nd.a >= i || nd.b >= i) { *err = "BVH branch child index out of range"; return false; }
-        } else { *err = "BVH node kind must be 0 (leaf) or 1 (branch)"; return false; }
+        });
+        if (bad.load() == 1) { *err = "BVH leaf out of range (first/count)"; return false; }
+        if (bad.load() == 2) { *err = "BVH branch child index out of range"; return false; }
+        if (bad.load() == 3) { *err = "BVH node kind must be 0 (leaf) or 1 (branch)"; return false; }
     }
     const ort_bvh_node& root = bvh[n_nodes - 1];
     for (int k = 0; k < 3; k++) {
@@ -194,58 +225,81 @@ bool build_wide_bvh(const ort_bvh_node* bvh, int64_t n_nodes, int64_t n_tris, Wi
         float m = a > b ? a : b;
         out->max_abs[k] = std::isfinite(m) ? m : 0.0f;
     }
-
-    struct Pending { int64_t src; int32_t dst; int level; };
-    std::vector<Pending> queue;
-    out->nodes.emplace_back();
-    queue.push_back({n_nodes - 1, 0, 1});
     auto area = [&](int64_t id) {
         const ort_bvh_node& nd = bvh[id];
         float sx = nd.hi[0] - nd.lo[0], sy = nd.hi[1] - nd.lo[1], sz = nd.hi[2] - nd.lo[2];
         float a = sx * sy + sy * sz + sz * sx;
         return std::isfinite(a) ? a : 0.0f;
     };
-    for (size_t qi = 0; qi < queue.size(); qi++) {
-        Pending cur = queue[qi];
-        if (cur.level > out->depth) out->depth = cur.level;
-        int64_t kids[4];
-        int nk = 0;
-        if (bvh[cur.src].kind == 0) {
-            if (bvh[cur.src].b > 0) kids[nk++] = cur.src; // a lone (root) leaf; an empty leaf yields an empty node
-        } else {
-            kids[nk++] = bvh[cur.src].a;
-            kids[nk++] = bvh[cur.src].b;
-            while (nk < 4) { // open the largest inner child until the node is full
-                int pick = -1;
-                float best = -1.0f;
-                for (int i = 0; i < nk; i++)
-                    if (bvh[kids[i]].kind == 1 && area(kids[i]) > best) { best = area(kids[i]); pick = i; }
-                if (pick < 0) break;
-                int64_t open = kids[pick];
-                kids[pick] = bvh[open].a;
-                kids[nk++] = bvh[open].b;
+    struct Item { int64_t src; int64_t kids[4]; int nk; int n_inner; size_t child_off; };
+    std::vector<Item> level(1), next;
+    level[0].src = n_nodes - 1;
+    size_t level_base = 0; // index of the first node of this level in out->nodes
+    out->nodes.reserve((size_t)n_nodes / 2 + 16); // a wide node absorbs at least one binary branch besides its own: no regrowth copies
+    out->nodes.resize(1);
+    while (!level.empty()) {
+        out->depth++;
+        // 1. children of every node of the level (parallel)
+        par_for(level.size(), threads, 2048, [&](size_t f, size_t c) {
+            for (size_t i = f; i < f + c; i++) {
+                Item& it = level[i];
+                it.nk = 0;
+                if (bvh[it.src].kind == 0) {
+                    if (bvh[it.src].b > 0) it.kids[it.nk++] = it.src; // a lone (root) leaf; an empty leaf yields an empty node
+                } else {
+                    it.kids[it.nk++] = bvh[it.src].a;
+                    it.kids[it.nk++] = bvh[it.src].b;
+                    while (it.nk < 4) { // open the largest inner child until the node is full
+                        int pick = -1;
+                        float best = -1.0f;
+                        for (int k = 0; k < it.nk; k++)
+                            if (bvh[it.kids[k]].kind == 1 && area(it.kids[k]) > best) { best = area(it.kids[k]); pick = k; }
+                        if (pick < 0) break;
+                        const int64_t open = it.kids[pick];
+                        it.kids[pick] = bvh[open].a;
+                        it.kids[it.nk++] = bvh[open].b;
+                    }
+                }
+                it.n_inner = 0;
+                for (int k = 0; k < it.nk; k++)
+                    if (bvh[it.kids[k]].kind == 1) it.n_inner++;
             }
-        }
-        WideNode wn;
-        for (int i = 0; i < 4; i++) {
-            for (int ax = 0; ax < 3; ax++) { wn.bounds[ax][0][i] = kInf; wn.bounds[ax][1][i] = -kInf; }
-            wn.child[i] = WIDE_EMPTY;
-            wn.reserved[i] = 0;
-        }
-        for (int i = 0; i < nk; i++) {
-            const ort_bvh_node& c = bvh[kids[i]];
-            for (int ax = 0; ax < 3; ax++) { wn.bounds[ax][0][i] = c.lo[ax]; wn.bounds[ax][1][i] = c.hi[ax]; }
-            if (c.kind == 0) {
-                if (c.b == 0) continue; // empty leaf: leave the slot unused
-                wn.child[i] = ~(int32_t)((c.a << 3) | c.b);
-            } else {
-                if (out->nodes.size() >= (size_t)0x7fffffff) { *err = "wide BVH too large"; return false; }
-                wn.child[i] = (int32_t)out->nodes.size();
-                out->nodes.emplace_back();
-                queue.push_back({kids[i], wn.child[i], cur.level + 1});
+        });
+        // 2. output indices of the next level: exclusive scan in queue order
+        size_t n_next = 0;
+        for (Item& it : level) { it.child_off = n_next; n_next += (size_t)it.n_inner; }
+        const size_t next_base = level_base + level.size();
+        if (next_base + n_next >= (size_t)0x7fffffff) { *err = "wide BVH too large"; return false; }
+        out->nodes.resize(next_base + n_next);
+        next.resize(n_next);
+        // 3. emit the nodes of this level and the work items of the next one (parallel)
+        par_for(level.size(), threads, 2048, [&](size_t f, size_t c) {
+            for (size_t i = f; i < f + c; i++) {
+                const Item& it = level[i];
+                WideNode wn;
+                for (int k = 0; k < 4; k++) {
+                    for (int ax = 0; ax < 3; ax++) { wn.bounds[ax][0][k] = kInf; wn.bounds[ax][1][k] = -kInf; }
+                    wn.child[k] = WIDE_EMPTY;
+                    wn.reserved[k] = 0;
+                }
+                size_t inner = 0;
+                for (int k = 0; k < it.nk; k++) {
+                    const ort_bvh_node& ch = bvh[it.kids[k]];
+                    for (int ax = 0; ax < 3; ax++) { wn.bounds[ax][0][k] = ch.lo[ax]; wn.bounds[ax][1][k] = ch.hi[ax]; }
+                    if (ch.kind == 0) {
+                        if (ch.b == 0) continue; // empty leaf: leave the slot unused
+                        wn.child[k] = ~(int32_t)((ch.a << 3) | ch.b);
+                    } else {
+                        const size_t pos = it.child_off + inner++;
+                        wn.child[k] = (int32_t)(next_base + pos);
+                        next[pos].src = it.kids[k];
+                    }
+                }
+                out->nodes[level_base + i] = wn;
             }
-        }
-        out->nodes[cur.dst] = wn;
+        });
+        level_base = next_base;
+        level.swap(next);
     }
     // worst-case stack occupancy: F(node) = (#children - 1) + max F(inner child); children have
     // larger indices than their parent (breadth-first emission), so one reverse sweep suffices.
@@ -517,4 +571,18 @@ extern "C" int64_t ort_bvh_build(ort_triangle* tris, int64_t n, ort_bvh_node* no
     if (n) std::memcpy(tris, sorted.data(), sizeof(ort_triangle) * (size_t)n);
     std::memcpy(nodes_out, nodes.data(), sizeof(ort_bvh_node) * nodes.size());
     return (int64_t)nodes.size();
+}
+
+extern "C" int64_t ort_wide_bvh_emit(const ort_bvh_node* bvh, int64_t n_nodes, int64_t n_tris, int32_t threads,
+                                     void* nodes_out, int64_t cap, int32_t* depth, int32_t* max_stack) {
+    ort::WideBVH w;
+    const char* why = nullptr;
+    if (!ort::build_wide_bvh(bvh, n_nodes, n_tris, &w, &why, threads)) return -1;
+    if (depth) *depth = w.depth;
+    if (max_stack) *max_stack = w.max_stack;
+    if (nodes_out) {
+        if ((int64_t)w.nodes.size() > cap) return -2;
+        std::memcpy(nodes_out, w.nodes.data(), w.nodes.size() * sizeof(ort::WideNode));
+    }
+    return (int64_t)w.nodes.size();
 }

@@ -117,7 +117,8 @@ struct WideBVH {
 
 // Re-emit the reference's binary post-order BVH (root = last node, raytracer.odin:375) as a
 // 4-wide BVH.  Returns false (with *err set) on malformed input.
-bool build_wide_bvh(const ort_bvh_node* bvh, int64_t n_nodes, int64_t n_tris, WideBVH* out, const char** err);
+bool build_wide_bvh(const ort_bvh_node* bvh, int64_t n_nodes, int64_t n_tris, WideBVH* out, const char** err,
+                    int threads = 0 /* 0 = all host cores, at most 16 */);
 
 // Conservative 8-bit re-encoding of a WideNode array (same indices, same children).
 void quantize_wide_nodes(const WideNode* in, size_t n, QuantNode* out);

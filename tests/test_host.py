@@ -130,3 +130,32 @@ def test_output_and_partition(tmp_path):
         for (f0, c0), (f1, _) in zip(parts, parts[1:]):
             assert f0 + c0 == f1
         assert max(c for _, c in parts) - min(c for _, c in parts) <= 1
+
+
+def test_wide_bvh_emission_is_thread_count_independent(scene_dir):
+    """The level-synchronous parallel re-emission (ort_upload_scene's host stage) gives byte-identical
+    nodes, depth and stack bound on 1, 3 and 16 threads; breadth-first order, root = node 0."""
+    from tests.golden.make_golden import soup
+
+    lib = cabi.load_library()
+    s = gltf.read_gltf(scenegen.terrain(os.path.join(scene_dir, "wide_c4.gltf"), grid=120, n_spheres=40, subdiv=2, seed=3))
+    for tris in (soup(1, 5), soup(9, 6), soup(20000, 7), s.triangles.copy()):
+        nodes = native_bvh_build(tris)
+        outs = []
+        for threads in (1, 3, 16):
+            buf = np.zeros((2 * len(tris) + 4) * 128, np.uint8)
+            d, m = C.c_int32(), C.c_int32()
+            n = lib.ort_wide_bvh_emit(cabi.ptr(nodes), len(nodes), len(tris), threads, cabi.ptr(buf), len(buf) // 128,
+                                      C.byref(d), C.byref(m))
+            assert n > 0
+            outs.append((n, d.value, m.value, buf[: n * 128].tobytes()))
+        assert outs[0] == outs[1] == outs[2]
+        n, depth, max_stack, raw = outs[0]
+        child = np.frombuffer(raw, np.int32).reshape(n, 32)[:, 24:28]
+        inner = child[(child >= 0)]
+        assert sorted(inner.tolist()) == list(range(1, n))  # every node but the root is referenced exactly once
+        assert np.all(child[child >= 0].reshape(-1) > np.repeat(np.arange(n), 4).reshape(n, 4)[child >= 0])  # children after parents
+        leaves = child[(child < 0) & (child != np.int32(-2**31))]
+        cnt = (~leaves) & 7
+        assert cnt.sum() == len(tris) and 1 <= depth <= max_stack
+    assert lib.ort_wide_bvh_emit(cabi.ptr(nodes), 0, len(tris), 1, None, 0, None, None) == -1
