@@ -217,6 +217,37 @@ int staged_upload(ort_ctx* ctx, void* d_dst, size_t n, size_t item, size_t min_p
     return 0;
 }
 
+// Same, for K record types derived from the SAME source items in one pass (the 168-byte triangles are
+// read once, not once per record type): fill(first, count, outs[K]) writes record type j of item
+// first + i to (char*)outs[j] + i * item[j].
+template <int K, typename F>
+int staged_upload_multi(ort_ctx* ctx, void* const (&d_dst)[K], const size_t (&item)[K], size_t n, size_t min_per_thread, F fill) {
+    if (n == 0) return 0;
+    if (ensure_stage(ctx)) return 1;
+    size_t total = 0;
+    for (int j = 0; j < K; j++) total += item[j];
+    const size_t per_chunk = std::max<size_t>(1, ort_ctx::STAGE_BYTES / total);
+    for (size_t off = 0; off < n; off += per_chunk) {
+        const size_t cnt = std::min(per_chunk, n - off);
+        const int slot = ctx->stage_next;
+        ctx->stage_next = (slot + 1) % ort_ctx::STAGE_SLOTS;
+        char* h = ctx->stage + (size_t)slot * ort_ctx::STAGE_BYTES;
+        char* region[K];
+        size_t acc = 0;
+        for (int j = 0; j < K; j++) { region[j] = h + acc; acc += item[j] * per_chunk; }
+        CK(cudaEventSynchronize(ctx->stage_ev[slot]));
+        parallel_for(ctx, cnt, min_per_thread, [&](size_t a, size_t c) {
+            void* outs[K];
+            for (int j = 0; j < K; j++) outs[j] = region[j] + a * item[j];
+            fill(off + a, c, outs);
+        });
+        for (int j = 0; j < K; j++)
+            if (d_dst[j]) CK(cudaMemcpyAsync((char*)d_dst[j] + off * item[j], region[j], cnt * item[j], cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaEventRecord(ctx->stage_ev[slot], ctx->stream));
+    }
+    return 0;
+}
+
 // texture_index (textures.odin:79-104) applied to every texel on the host: u8 -> /255, missing
 // channels = 1, optional pow(rgb, 2.2); the result is what a point fetch returns on the device.
 int make_texture(ort_ctx* ctx, const ort_texture& t, bool srgb, cudaTextureObject_t* out) {
@@ -751,68 +782,60 @@ int ort_upload_scene(ort_ctx* ctx, const ort_scene* sc) {
                       [&](size_t f, size_t c, void* o) { std::memcpy(o, mats.data() + f, c * sizeof(DevMaterial)); }))
         return 1;
 
-    // traversal records: scene triangles, then the light triangles (a ray walks both trees with the same code)
-    if (scene_buffer(ctx, ort_ctx::SB_TRIS, (nt + nlt) * sizeof(TriIsect), &d)) return 1;
-    sd.tris = (const float4*)d;
-    sd.ltris = sd.tris + nt * 4;
-    sd.light_tri_base = (uint32_t)nt;
-    if (staged_upload(ctx, d, nt, sizeof(TriIsect), 4096,
-                      [&](size_t f, size_t c, void* o) { make_isect_records(sc->triangles + f, (int64_t)c, (TriIsect*)o); }))
-        return 1;
-    if (staged_upload(ctx, (char*)d + nt * sizeof(TriIsect), nlt, sizeof(TriIsect), 4096,
-                      [&](size_t f, size_t c, void* o) { make_isect_records(sc->light_triangles + f, (int64_t)c, (TriIsect*)o); }))
-        return 1;
-    if (scene_buffer(ctx, ort_ctx::SB_LLIGHT, nlt * sizeof(TriLight), &d)) return 1;
-    sd.llight = (const float4*)d;
-    if (staged_upload(ctx, d, nlt, sizeof(TriLight), 4096,
-                      [&](size_t f, size_t c, void* o) { make_light_records(sc->light_triangles + f, (int64_t)c, (TriLight*)o); }))
-        return 1;
-    pt.mark("isect");
-
-    // shading records (+ the material_index range check of every triangle)
+    // per-triangle records of the scene triangles, all in ONE pass over the 168-byte source structs:
+    // traversal (TriIsect), shading (TriShade, + the material_index range check), and — only when a
+    // material needs them — texture coordinates (TriUV) and tangents (TriTan).  The traversal array
+    // continues with the light triangles (a ray walks both trees with the same code).
     std::atomic<int> bad_material{0};
-    if (scene_buffer(ctx, ort_ctx::SB_TSHADE, nt * sizeof(TriShade), &d)) return 1;
-    sd.tshade = (const float4*)d;
-    if (staged_upload(ctx, d, nt, sizeof(TriShade), 4096, [&](size_t f, size_t c, void* o) {
-            TriShade* rec = (TriShade*)o;
-            for (size_t i = 0; i < c; i++) {
-                const ort_triangle& t = sc->triangles[f + i];
-                TriShade& r = rec[i];
-                std::memcpy(r.n1, t.n1, 12); std::memcpy(r.n2, t.n2, 12); std::memcpy(r.n3, t.n3, 12);
-                r.ngx = t.ng[0]; r.ngy = t.ng[1]; r.ngz = t.ng[2];
-                if (t.material_index < 0 || t.material_index >= sc->n_materials) bad_material.store(1, std::memory_order_relaxed);
-                r.material = (int32_t)t.material_index; r.flags = 0; r.pad0 = r.pad1 = 0;
-            }
-        }))
-        return 1;
-    if (bad_material.load()) { cudaStreamSynchronize(ctx->stream); return fail(ctx, "triangle material_index out of range"); }
-    if (any_tex) {
-        if (scene_buffer(ctx, ort_ctx::SB_TUV, nt * sizeof(TriUV), &d)) return 1;
-        sd.tuv = (const float4*)d;
-        if (staged_upload(ctx, d, nt, sizeof(TriUV), 4096, [&](size_t f, size_t c, void* o) {
-                TriUV* rec = (TriUV*)o;
+    {
+        void* d_isect = nullptr; void* d_shade = nullptr; void* d_uv = nullptr; void* d_tan = nullptr;
+        if (scene_buffer(ctx, ort_ctx::SB_TRIS, (nt + nlt) * sizeof(TriIsect), &d_isect)) return 1;
+        if (scene_buffer(ctx, ort_ctx::SB_TSHADE, nt * sizeof(TriShade), &d_shade)) return 1;
+        if (any_tex && scene_buffer(ctx, ort_ctx::SB_TUV, nt * sizeof(TriUV), &d_uv)) return 1;
+        if (any_normal && scene_buffer(ctx, ort_ctx::SB_TTAN, nt * sizeof(TriTan), &d_tan)) return 1;
+        sd.tris = (const float4*)d_isect;
+        sd.ltris = sd.tris + nt * 4;
+        sd.light_tri_base = (uint32_t)nt;
+        sd.tshade = (const float4*)d_shade;
+        sd.tuv = (const float4*)d_uv;
+        sd.ttan = (const float4*)d_tan;
+        void* const dsts[4] = {d_isect, d_shade, d_uv, d_tan};
+        const size_t items[4] = {sizeof(TriIsect), sizeof(TriShade), any_tex ? sizeof(TriUV) : 0, any_normal ? sizeof(TriTan) : 0};
+        const bool want_uv = any_tex, want_tan = any_normal;
+        if (staged_upload_multi<4>(ctx, dsts, items, nt, 4096, [&](size_t f, size_t c, void** outs) {
+                make_isect_records(sc->triangles + f, (int64_t)c, (TriIsect*)outs[0]);
+                TriShade* rs = (TriShade*)outs[1];
+                TriUV* ru = (TriUV*)outs[2];
+                TriTan* rt = (TriTan*)outs[3];
                 for (size_t i = 0; i < c; i++) {
                     const ort_triangle& t = sc->triangles[f + i];
-                    TriUV& r = rec[i];
-                    std::memcpy(r.tex1, t.tex1, 8); std::memcpy(r.tex2, t.tex2, 8); std::memcpy(r.tex3, t.tex3, 8);
-                    r.pad[0] = r.pad[1] = 0;
+                    TriShade& r = rs[i];
+                    std::memcpy(r.n1, t.n1, 12); std::memcpy(r.n2, t.n2, 12); std::memcpy(r.n3, t.n3, 12);
+                    r.ngx = t.ng[0]; r.ngy = t.ng[1]; r.ngz = t.ng[2];
+                    if (t.material_index < 0 || t.material_index >= sc->n_materials) bad_material.store(1, std::memory_order_relaxed);
+                    r.material = (int32_t)t.material_index; r.flags = 0; r.pad0 = r.pad1 = 0;
+                    if (want_uv) {
+                        TriUV& u = ru[i];
+                        std::memcpy(u.tex1, t.tex1, 8); std::memcpy(u.tex2, t.tex2, 8); std::memcpy(u.tex3, t.tex3, 8);
+                        u.pad[0] = u.pad[1] = 0;
+                    }
+                    if (want_tan) {
+                        std::memcpy(rt[i].tan1, t.tan1, 16); std::memcpy(rt[i].tan2, t.tan2, 16); std::memcpy(rt[i].tan3, t.tan3, 16);
+                    }
                 }
             }))
             return 1;
-    }
-    if (any_normal) {
-        if (scene_buffer(ctx, ort_ctx::SB_TTAN, nt * sizeof(TriTan), &d)) return 1;
-        sd.ttan = (const float4*)d;
-        if (staged_upload(ctx, d, nt, sizeof(TriTan), 4096, [&](size_t f, size_t c, void* o) {
-                TriTan* rec = (TriTan*)o;
-                for (size_t i = 0; i < c; i++) {
-                    const ort_triangle& t = sc->triangles[f + i];
-                    std::memcpy(rec[i].tan1, t.tan1, 16); std::memcpy(rec[i].tan2, t.tan2, 16); std::memcpy(rec[i].tan3, t.tan3, 16);
-                }
-            }))
+        if (bad_material.load()) { cudaStreamSynchronize(ctx->stream); return fail(ctx, "triangle material_index out of range"); }
+        if (staged_upload(ctx, (char*)d_isect + nt * sizeof(TriIsect), nlt, sizeof(TriIsect), 4096,
+                          [&](size_t f, size_t c, void* o) { make_isect_records(sc->light_triangles + f, (int64_t)c, (TriIsect*)o); }))
+            return 1;
+        if (scene_buffer(ctx, ort_ctx::SB_LLIGHT, nlt * sizeof(TriLight), &d)) return 1;
+        sd.llight = (const float4*)d;
+        if (staged_upload(ctx, d, nlt, sizeof(TriLight), 4096,
+                          [&](size_t f, size_t c, void* o) { make_light_records(sc->light_triangles + f, (int64_t)c, (TriLight*)o); }))
             return 1;
     }
-    pt.mark("shade_records");
+    pt.mark("triangle_records");
     {
         std::vector<DevTexture> texs((size_t)sc->n_textures);
         for (int64_t i = 0; i < sc->n_textures; i++) {
