@@ -270,7 +270,8 @@ struct Loader {
                         cof[r][c] = ((r + c) % 2 == 0) ? minor : -minor;
                     }
                 const size_t num_vertices = has_i ? idx.count : pos.count;
-                scene->triangles.reserve(scene->triangles.size() + num_vertices / 3);
+                if (scene->triangles.capacity() < scene->triangles.size() + num_vertices / 3) // geometric growth: an exact
+                    scene->triangles.reserve(std::max(scene->triangles.size() + num_vertices / 3, 2 * scene->triangles.capacity())); // reserve per primitive is quadratic
                 for (size_t i = 0; i < num_vertices / 3; i++) {
                     float P[3][3], N[3][3] = {}, UV[3][2] = {}, T[3][4] = {};
                     for (size_t k = 0; k < 3; k++) {

@@ -43,6 +43,19 @@ def test_native_loader_equals_python_loader(scene_dir, name):
     _same_scene(a, b, finished=True)
 
 
+def test_native_loader_full_size_c4(scene_dir):
+    """BASELINE config 4 at full size (1 000 480 triangles in 392 primitives): bit-identical to the Python
+    loader, and in about a second (a per-primitive exact reserve once made this quadratic: 50 s)."""
+    import time
+
+    p = scenegen.terrain(os.path.join(scene_dir, "cpp_c4_full.gltf"))
+    t0 = time.perf_counter()
+    b = hostlib.read_gltf(p)
+    dt = time.perf_counter() - t0
+    assert len(b.triangles) == 1_000_480 and dt < 15.0, dt
+    _same_scene(gltf.read_gltf(p), b)
+
+
 def test_native_textures_png_and_hdr(scene_dir, tmp_path):
     p = scenegen.textured(os.path.join(scene_dir, "cpp_c3.gltf"), tex_res=64, detail=0.15)
     env = scenegen.write_env_hdr(os.path.join(scene_dir, "cpp_env.hdr"), 128, 64)
