@@ -510,7 +510,7 @@ int render_impl(ort_ctx* ctx, uint32_t w, uint32_t h, int32_t depth, uint64_t fi
     for (;;) {
         const uint64_t n_waves = (n_samples + per_wave - 1) / per_wave;
         pipes = std::max(1, std::min(ctx->overlap, MAX_PIPES));
-        if (ctx->profiling || interrupt || depth == 0) pipes = 1;
+        if (ctx->profiling || depth == 0) pipes = 1;
         if ((uint64_t)pipes > n_waves) pipes = (int)n_waves;
         if (ensure_paths(ctx, (int64_t)(per_wave * npix), pipes) == 0) break;
         // not enough free HBM for this many paths in flight (other contexts / processes on the GPU):
@@ -540,6 +540,10 @@ int render_impl(ort_ctx* ctx, uint32_t w, uint32_t h, int32_t depth, uint64_t fi
         p.n_batch_samples = (uint32_t)nb;
         const int pi = (int)(wave % (uint64_t)pipes);
         cudaStream_t st = pi ? ctx->aux_stream[pi] : ctx->stream;
+        // with an interrupt flag the host stays at most `pipes` waves ahead of the device (it waits for
+        // the wave that last used this pipeline), so the poll above sees a SIGINT within a few waves
+        // while the pipelines still overlap
+        if (interrupt && wave >= (uint64_t)pipes) CK(cudaEventSynchronize(ctx->ps[pi].resolved));
         if (depth == 0) {
             // raytrace(depth_left = 0) returns 0 (raytracer.odin:433): count the samples, add nothing
             CK(cudaMemsetAsync(ctx->ps[0].st_c, 0, (size_t)(nb * npix) * 16, ctx->stream));
@@ -553,7 +557,6 @@ int render_impl(ort_ctx* ctx, uint32_t w, uint32_t h, int32_t depth, uint64_t fi
         prev = ctx->ps[pi].resolved;
         done += nb;
         wave++;
-        if (interrupt) CK(cudaStreamSynchronize(ctx->stream)); // keep the poll granular: one wave
     }
     for (int i = 1; i < pipes; i++) {
         CK(cudaEventRecord(ctx->ev_join[i], ctx->aux_stream[i]));
