@@ -1,11 +1,13 @@
 // gltf.cpp — read_gltf / populate_scene (input.odin:13-259) and finish_scene (raytracer.odin:62-91)
 // for the C++ host.  Arithmetic is f32 with every operation individually rounded (the file is
 // compiled with -ffp-contract=off), sums taken left to right like a generic matrix product.
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <limits>
 #include <map>
+#include <thread>
 
 #include "json.hpp"
 #include "scene.hpp"
@@ -207,6 +209,26 @@ struct Loader {
         return true;
     }
 
+    // triangles the hierarchy under `node_idx` will emit (one pre-pass, so the triangle array is allocated once)
+    size_t count_triangles(int64_t node_idx, int depth) const {
+        if (depth > 512) return 0;
+        const Json& node = j.at("nodes").at((size_t)node_idx);
+        if (node_idx < 0 || node.is_null()) return 0;
+        size_t n = 0;
+        if (node.has("mesh")) {
+            const Json& prims = j.at("meshes").at((size_t)node.at("mesh").integer(-1)).at("primitives");
+            for (size_t pi = 0; pi < prims.size(); pi++) {
+                const Json& prim = prims.at(pi);
+                const Json& acc = j.at("accessors").at((size_t)(prim.has("indices") ? prim.at("indices").integer(-1)
+                                                                                    : prim.at("attributes").at("POSITION").integer(-1)));
+                n += (size_t)std::max<int64_t>(acc.at("count").integer(0), 0) / 3;
+            }
+        }
+        const Json& kids = node.at("children");
+        for (size_t k = 0; k < kids.size(); k++) n += count_triangles(kids.at(k).integer(-1), depth + 1);
+        return n;
+    }
+
     bool populate(int64_t node_idx, const Mat4& parent, int depth) { // populate_scene input.odin:92-233
         if (depth > 512) return fail("node hierarchy too deep (cycle?)");
         const Json& node = j.at("nodes").at((size_t)node_idx);
@@ -270,55 +292,80 @@ struct Loader {
                         cof[r][c] = ((r + c) % 2 == 0) ? minor : -minor;
                     }
                 const size_t num_vertices = has_i ? idx.count : pos.count;
-                if (scene->triangles.capacity() < scene->triangles.size() + num_vertices / 3) // geometric growth: an exact
-                    scene->triangles.reserve(std::max(scene->triangles.size() + num_vertices / 3, 2 * scene->triangles.capacity())); // reserve per primitive is quadratic
-                for (size_t i = 0; i < num_vertices / 3; i++) {
-                    float P[3][3], N[3][3] = {}, UV[3][2] = {}, T[3][4] = {};
-                    for (size_t k = 0; k < 3; k++) {
-                        const size_t index = has_i ? (size_t)read_index(idx, i * 3 + k) : i * 3 + k;
-                        if (index >= pos.count) return fail("Failed to read position data from accessor");
-                        float raw[4];
-                        read_float(pos, index, raw, 3);
-                        const float v4[4] = {raw[0], raw[1], raw[2], 1.0f};
-                        mul_vec(transform, v4, P[k]);
-                        if (has_n) {
-                            if (index >= nrm.count) return fail("Failed to read normal data from accessor");
-                            read_float(nrm, index, raw, 3);
-                            for (int r = 0; r < 3; r++) N[k][r] = (cof[r][0] * raw[0] + cof[r][1] * raw[1]) + cof[r][2] * raw[2];
-                            normalize3(N[k]);
+                const size_t n_new = num_vertices / 3, first_out = scene->triangles.size();
+                if (scene->triangles.capacity() < first_out + n_new) // geometric growth: an exact reserve per primitive is quadratic
+                    scene->triangles.reserve(std::max(first_out + n_new, 2 * scene->triangles.capacity()));
+                scene->triangles.resize(first_out + n_new);
+                ort_triangle* out_tris = scene->triangles.data() + first_out;
+                std::atomic<int> bad{0}; // 1 position, 2 normal, 3 uv, 4 tangent index out of range
+                auto work = [&](size_t t0, size_t t1) {
+                    for (size_t i = t0; i < t1; i++) {
+                        float P[3][3], N[3][3] = {}, UV[3][2] = {}, T[3][4] = {};
+                        for (size_t k = 0; k < 3; k++) {
+                            const size_t index = has_i ? (size_t)read_index(idx, i * 3 + k) : i * 3 + k;
+                            if (index >= pos.count) { bad.store(1); return; }
+                            float raw[4];
+                            read_float(pos, index, raw, 3);
+                            const float v4[4] = {raw[0], raw[1], raw[2], 1.0f};
+                            mul_vec(transform, v4, P[k]);
+                            if (has_n) {
+                                if (index >= nrm.count) { bad.store(2); return; }
+                                read_float(nrm, index, raw, 3);
+                                for (int r = 0; r < 3; r++) N[k][r] = (cof[r][0] * raw[0] + cof[r][1] * raw[1]) + cof[r][2] * raw[2];
+                                normalize3(N[k]);
+                            }
+                            if (has_uv) {
+                                if (index >= uv.count) { bad.store(3); return; }
+                                read_float(uv, index, UV[k], 2);
+                            }
+                            float t4[4] = {0, 0, 0, 0};
+                            if (has_t) {
+                                if (index >= tan.count) { bad.store(4); return; }
+                                read_float(tan, index, t4, 4);
+                            }
+                            // tangents[i].xyz = normalize((transform * {t, 0}).xyz): a zero tangent becomes NaN (:193-195)
+                            const float tv[4] = {t4[0], t4[1], t4[2], 0.0f};
+                            mul_vec(transform, tv, T[k]);
+                            normalize3(T[k]);
+                            T[k][3] = t4[3];
                         }
-                        if (has_uv) {
-                            if (index >= uv.count) return fail("Failed to read UV data from accessor");
-                            read_float(uv, index, UV[k], 2);
+                        ort_triangle tri{};
+                        float e1[3], e2[3], ng[3];
+                        for (int r = 0; r < 3; r++) { e1[r] = P[1][r] - P[0][r]; e2[r] = P[2][r] - P[0][r]; }
+                        ng[0] = e1[1] * e2[2] - e1[2] * e2[1];
+                        ng[1] = e1[2] * e2[0] - e1[0] * e2[2];
+                        ng[2] = e1[0] * e2[1] - e1[1] * e2[0];
+                        normalize3(ng);
+                        for (int r = 0; r < 3; r++) {
+                            tri.p[r] = P[0][r]; tri.u[r] = e1[r]; tri.v[r] = e2[r]; tri.ng[r] = ng[r];
+                            tri.n1[r] = has_n ? N[0][r] : ng[r];
+                            tri.n2[r] = has_n ? N[1][r] : ng[r];
+                            tri.n3[r] = has_n ? N[2][r] : ng[r];
                         }
-                        float t4[4] = {0, 0, 0, 0};
-                        if (has_t) {
-                            if (index >= tan.count) return fail("Failed to read tangent data from accessor");
-                            read_float(tan, index, t4, 4);
-                        }
-                        // tangents[i].xyz = normalize((transform * {t, 0}).xyz): a zero tangent becomes NaN (:193-195)
-                        const float tv[4] = {t4[0], t4[1], t4[2], 0.0f};
-                        mul_vec(transform, tv, T[k]);
-                        normalize3(T[k]);
-                        T[k][3] = t4[3];
+                        std::memcpy(tri.tex1, UV[0], 8); std::memcpy(tri.tex2, UV[1], 8); std::memcpy(tri.tex3, UV[2], 8);
+                        std::memcpy(tri.tan1, T[0], 16); std::memcpy(tri.tan2, T[1], 16); std::memcpy(tri.tan3, T[2], 16);
+                        tri.material_index = material_index;
+                        out_tris[i] = tri;
                     }
-                    ort_triangle tri{};
-                    float e1[3], e2[3], ng[3];
-                    for (int r = 0; r < 3; r++) { e1[r] = P[1][r] - P[0][r]; e2[r] = P[2][r] - P[0][r]; }
-                    ng[0] = e1[1] * e2[2] - e1[2] * e2[1];
-                    ng[1] = e1[2] * e2[0] - e1[0] * e2[2];
-                    ng[2] = e1[0] * e2[1] - e1[1] * e2[0];
-                    normalize3(ng);
-                    for (int r = 0; r < 3; r++) {
-                        tri.p[r] = P[0][r]; tri.u[r] = e1[r]; tri.v[r] = e2[r]; tri.ng[r] = ng[r];
-                        tri.n1[r] = has_n ? N[0][r] : ng[r];
-                        tri.n2[r] = has_n ? N[1][r] : ng[r];
-                        tri.n3[r] = has_n ? N[2][r] : ng[r];
+                };
+                // big primitives are flattened on several host threads (disjoint output ranges)
+                const size_t nthr = n_new >= 65536 ? std::min<size_t>(16, std::max(1u, std::thread::hardware_concurrency())) : 1;
+                if (nthr <= 1) work(0, n_new);
+                else {
+                    std::vector<std::thread> pool;
+                    const size_t per = (n_new + nthr - 1) / nthr;
+                    for (size_t t = 0; t < nthr; t++) {
+                        const size_t a = t * per, b = std::min(n_new, a + per);
+                        if (a < b) pool.emplace_back(work, a, b);
                     }
-                    std::memcpy(tri.tex1, UV[0], 8); std::memcpy(tri.tex2, UV[1], 8); std::memcpy(tri.tex3, UV[2], 8);
-                    std::memcpy(tri.tan1, T[0], 16); std::memcpy(tri.tan2, T[1], 16); std::memcpy(tri.tan3, T[2], 16);
-                    tri.material_index = material_index;
-                    scene->triangles.push_back(tri);
+                    for (auto& th : pool) th.join();
+                }
+                switch (bad.load()) {
+                case 1: return fail("Failed to read position data from accessor");
+                case 2: return fail("Failed to read normal data from accessor");
+                case 3: return fail("Failed to read UV data from accessor");
+                case 4: return fail("Failed to read tangent data from accessor");
+                default: break;
                 }
             }
         }
@@ -366,6 +413,12 @@ bool read_gltf(const std::string& path, HostScene* out, std::string* err) {
     const Json* roots = nullptr;
     if (L.j.has("scene")) roots = &L.j.at("scenes").at((size_t)L.j.at("scene").integer(0)).at("nodes"); // input.odin:236-248
     else if (L.j.at("scenes").size() > 0) roots = &L.j.at("scenes").at((size_t)0).at("nodes");
+    {
+        size_t total = 0;
+        if (roots) for (size_t i = 0; i < roots->size(); i++) total += L.count_triangles(roots->at(i).integer(-1), 0);
+        else for (size_t i = 0; i < L.j.at("nodes").size(); i++) total += L.count_triangles((int64_t)i, 0);
+        if (total < ((size_t)1 << 31)) out->triangles.reserve(total);
+    }
     bool ok = true;
     if (roots) {
         for (size_t i = 0; ok && i < roots->size(); i++) ok = L.populate(roots->at(i).integer(-1), ident, 0);
