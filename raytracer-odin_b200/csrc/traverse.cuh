@@ -17,9 +17,16 @@
 //   * The light BVH is appended to the scene's node / triangle arrays.  When a continuation ray's
 //     closest-hit stack runs dry the lane switches to phase 1 and walks the light tree with the
 //     same inner loop (no distance culling, no ordering needed) for the all-hit sum.
-//   * 4-wide nodes of one 128-byte line, near / far planes picked by per-ray byte offsets, 16-byte
-//     loads only; stack: first SMEM_STACK entries in shared memory ([entry][thread], conflict
-//     free), deeper entries in thread-local memory (exact worst case checked on the host).
+//   * 4-wide nodes of one 128-byte line read with 3 x LDG.256 (lo | hi planes of an axis) + 1 x LDG.128
+//     (children), near / far planes picked in registers; stack entries are 64-bit (node, entry
+//     distance): the first SMEM_STACK per thread in shared memory ([entry][thread], conflict free, one
+//     LDS.64 / STS.64 per pop / push), deeper ones in thread-local memory (exact worst case checked on
+//     the host); popped entries farther than the current best hit are skipped without a node fetch.
+//   * What bounds it, measured (profiles/r1_sensitivity.md): ~5 warp-level L2 round trips per ray, each
+//     waiting for the slowest of ~13 divergent lanes, at the knee of the occupancy curve (7 CTAs / SM).
+//     Extra L1-hit loads are free, +40 % ALU per visit costs 15 %, prefetching and batched triangle loads
+//     are slower, an 8-wide layout (traverse8.cuh) loses on the exact triangle solve.  What helped last:
+//     queue ORDER — a warp's primary rays are 2x2 pixels x 8 samples (k_raygen).
 //
 // Numerics: box tests are conservative supersets of the reference's (see make_ray); the triangle
 // solve is the reference's arithmetic bit for bit (tri_det_t / tri_uv); triangles of a leaf are
