@@ -318,6 +318,79 @@ bool build_wide_bvh(const ort_bvh_node* bvh, int64_t n_nodes, int64_t n_tris, Wi
     return true;
 }
 
+bool build_wide8x_bvh(const ort_bvh_node* bvh, int64_t n_nodes, int64_t n_tris, Wide8xBVH* out, const char** err) {
+    out->nodes.clear();
+    out->depth = 0;
+    out->max_stack = 0;
+    if (n_nodes <= 0) { *err = "empty BVH node array"; return false; }
+    struct Pending { int64_t src; int32_t dst; int level; };
+    std::vector<Pending> queue;
+    out->nodes.emplace_back();
+    queue.push_back({n_nodes - 1, 0, 1});
+    auto area = [&](int64_t id) {
+        const ort_bvh_node& nd = bvh[id];
+        float sx = nd.hi[0] - nd.lo[0], sy = nd.hi[1] - nd.lo[1], sz = nd.hi[2] - nd.lo[2];
+        float a = sx * sy + sy * sz + sz * sx;
+        return std::isfinite(a) ? a : 0.0f;
+    };
+    for (size_t qi = 0; qi < queue.size(); qi++) {
+        const Pending cur = queue[qi];
+        if (cur.level > out->depth) out->depth = cur.level;
+        int64_t kids[8];
+        int nk = 0;
+        if (bvh[cur.src].kind == 0) {
+            if (bvh[cur.src].b > 0) kids[nk++] = cur.src;
+        } else {
+            kids[nk++] = bvh[cur.src].a;
+            kids[nk++] = bvh[cur.src].b;
+            while (nk < 8) {
+                int pick = -1;
+                float best = -1.0f;
+                for (int i = 0; i < nk; i++)
+                    if (bvh[kids[i]].kind == 1 && area(kids[i]) > best) { best = area(kids[i]); pick = i; }
+                if (pick < 0) break;
+                const int64_t open = kids[pick];
+                kids[pick] = bvh[open].a;
+                kids[nk++] = bvh[open].b;
+            }
+        }
+        Wide8xNode wn;
+        std::memset(&wn, 0, sizeof wn);
+        for (int k = 0; k < 8; k++) {
+            for (int ax = 0; ax < 3; ax++) { wn.bounds[ax][0][k] = kInf; wn.bounds[ax][1][k] = -kInf; }
+            wn.child[k] = WIDE_EMPTY;
+        }
+        for (int k = 0; k < nk; k++) {
+            const ort_bvh_node& c = bvh[kids[k]];
+            for (int ax = 0; ax < 3; ax++) { wn.bounds[ax][0][k] = c.lo[ax]; wn.bounds[ax][1][k] = c.hi[ax]; }
+            if (c.kind == 0) {
+                if (c.a < 0 || c.b < 0 || c.b > 7 || c.a + c.b > n_tris) { *err = "BVH leaf out of range (first/count)"; return false; }
+                if (c.b == 0) continue;
+                wn.child[k] = ~(int32_t)((c.a << 3) | c.b);
+            } else {
+                if (out->nodes.size() >= (size_t)0x7fffffff) { *err = "wide BVH too large"; return false; }
+                wn.child[k] = (int32_t)out->nodes.size();
+                out->nodes.emplace_back();
+                queue.push_back({kids[k], wn.child[k], cur.level + 1});
+            }
+        }
+        out->nodes[cur.dst] = wn;
+    }
+    std::vector<int> need(out->nodes.size(), 0);
+    for (int64_t i = (int64_t)out->nodes.size() - 1; i >= 0; i--) {
+        int c = 0, deepest = 0;
+        for (int k = 0; k < 8; k++) {
+            const int32_t ch = out->nodes[i].child[k];
+            if (ch == WIDE_EMPTY) continue;
+            c++;
+            if (ch >= 0 && need[ch] > deepest) deepest = need[ch];
+        }
+        need[i] = (c > 0 ? c - 1 : 0) + deepest;
+    }
+    out->max_stack = need[0] + 1;
+    return true;
+}
+
 bool build_wide8_bvh(const ort_bvh_node* bvh, int64_t n_nodes, int64_t n_tris, Wide8BVH* out, const char** err) {
     out->nodes.clear();
     out->tri_order.clear();

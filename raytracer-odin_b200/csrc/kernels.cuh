@@ -65,6 +65,9 @@ struct SceneDev {
     const float4* nodes8;
     const float4* tris8;
     int32_t light_root8;
+    // exact-order 8-wide re-emission (Wide8xNode[], child references like WideNode; k_trace<.., .., 2>)
+    const float4* nodes8x;
+    int32_t light_root8x;
 };
 
 struct RenderParams {

@@ -42,7 +42,7 @@ struct ort_ctx {
     // re-uploading a scene of the same shape performs no cudaMalloc / cudaFree (a cudaFree was
     // measured at 15-600 ms on B200 boxes: it synchronises the device and unmaps).
     struct DevBuf { void* p = nullptr; size_t cap = 0, used = 0; };
-    enum { SB_NODES, SB_TRIS, SB_LLIGHT, SB_MATS, SB_TSHADE, SB_TUV, SB_TTAN, SB_TEXS, SB_NODES8, SB_TRIS8, SB_COUNT };
+    enum { SB_NODES, SB_TRIS, SB_LLIGHT, SB_MATS, SB_TSHADE, SB_TUV, SB_TTAN, SB_TEXS, SB_NODES8, SB_TRIS8, SB_NODES8X, SB_COUNT };
     DevBuf sbuf[SB_COUNT];
     struct TexSlot { cudaArray_t arr = nullptr; cudaTextureObject_t obj = 0; size_t w = 0, h = 0; bool in_use = false; };
     std::vector<TexSlot> tex_pool;
@@ -56,6 +56,9 @@ struct ort_ctx {
     int64_t n_tris = 0, n_ltris = 0;
     WideBVH wide, lwide;
     Wide8BVH wide8, lwide8;
+    Wide8xBVH wide8x, lwide8x;
+    bool use8x = false; // ORT_BVH8=2: exact-order 8-wide traversal (k_trace<.., .., 2>)
+    int trace8x_grid[2] = {0, 0};
     int bvh8 = 0;      // env ORT_BVH8=1: traverse the 8-wide re-emission (k_trace8)
     bool use8 = false; // the uploaded scene has an 8-wide tree
     int trace8_grid[2] = {0, 0};
@@ -383,6 +386,12 @@ void launch_trace(ort_ctx* ctx, ort_ctx::PathSet& P, cudaStream_t st, const floa
     a.qo = qo; a.qd = qd; a.n_ptr = n_ptr; a.work_ctr = work_ctr; a.index = index;
     a.hits = P.hits; a.lsum = lsum ? lsum : P.lsum;
     a.refill_threshold = ctx->refill; a.inner_min = ctx->inner_min;
+    if (ctx->use8x && mode < 2) {
+        if (mode == 0) k_trace<true, false, 2><<<ctx->trace8x_grid[0], TRACE_THREADS, 0, st>>>(ctx->sd, a);
+        else k_trace<false, true, 2><<<ctx->trace8x_grid[1], TRACE_THREADS, 0, st>>>(ctx->sd, a);
+        ctx->launches++;
+        return;
+    }
     if (ctx->use8 && mode < 2) {
         if (mode == 0) k_trace8<true><<<ctx->trace8_grid[0], TRACE_THREADS, 0, st>>>(ctx->sd, a);
         else k_trace8<false><<<ctx->trace8_grid[1], TRACE_THREADS, 0, st>>>(ctx->sd, a);
@@ -668,6 +677,10 @@ int ort_create(ort_ctx** out, const ort_device_cfg* cfg) {
     ORT_OCC(0, 0, true, false, false) ORT_OCC(0, 1, false, true, false) ORT_OCC(0, 2, true, true, false)
     ORT_OCC(1, 0, true, false, true) ORT_OCC(1, 1, false, true, true) ORT_OCC(1, 2, true, true, true)
 #undef ORT_OCC
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<true, false, 2>, TRACE_THREADS, 0);
+    c->trace8x_grid[0] = c->sm_count * std::max(occ, 1);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<false, true, 2>, TRACE_THREADS, 0);
+    c->trace8x_grid[1] = c->sm_count * std::max(occ, 1);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace8<true>, TRACE_THREADS, 0);
     c->trace8_grid[0] = c->sm_count * std::max(occ, 1);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace8<false>, TRACE_THREADS, 0);
@@ -738,12 +751,19 @@ int ort_upload_scene(ort_ctx* ctx, const ort_scene* sc) {
     // builds and uploads the per-triangle records, which do not depend on it.
     const char* why_scene = nullptr;
     const char* why_light = nullptr;
-    bool ok_scene = false, ok_light = false, ok8 = false;
+    bool ok_scene = false, ok_light = false, ok8 = false, ok8x = false;
     std::thread wide_thread([&] {
         ok_scene = build_wide_bvh(sc->bvh, sc->n_bvh_nodes, sc->n_triangles, &ctx->wide, &why_scene);
         ok_light = build_wide_bvh(sc->light_bvh, sc->n_light_bvh_nodes, sc->n_light_triangles, &ctx->lwide, &why_light);
+        ok8x = false;
+        if (ctx->bvh8 == 2 && ok_scene && ok_light) {
+            const char* why8 = nullptr;
+            ok8x = build_wide8x_bvh(sc->bvh, sc->n_bvh_nodes, sc->n_triangles, &ctx->wide8x, &why8) &&
+                   build_wide8x_bvh(sc->light_bvh, sc->n_light_bvh_nodes, sc->n_light_triangles, &ctx->lwide8x, &why8) &&
+                   ctx->wide8x.max_stack <= MAX_STACK && ctx->lwide8x.max_stack <= MAX_STACK;
+        }
         ok8 = false;
-        if (ctx->bvh8 && ok_scene && ok_light) {
+        if (ctx->bvh8 == 1 && ok_scene && ok_light) {
             const char* why8 = nullptr; // e.g. leaves larger than the reference's 4: stay on the 4-wide tree
             ok8 = build_wide8_bvh(sc->bvh, sc->n_bvh_nodes, sc->n_triangles, &ctx->wide8, &why8) &&
                   build_wide8_bvh(sc->light_bvh, sc->n_light_bvh_nodes, sc->n_light_triangles, &ctx->lwide8, &why8) &&
@@ -911,6 +931,32 @@ int ort_upload_scene(ort_ctx* ctx, const ort_scene* sc) {
         }
         sd.nodes = (const float4*)d;
         sd.light_root = (int32_t)ns;
+    }
+    ctx->use8x = ok8x && !ctx->quant;
+    if (ctx->use8x) {
+        // exact-order 8-wide tree: scene nodes, then the light nodes with rebased references
+        const size_t ns8 = ctx->wide8x.nodes.size(), nl8 = ctx->lwide8x.nodes.size();
+        if (scene_buffer(ctx, ort_ctx::SB_NODES8X, (ns8 + nl8) * sizeof(Wide8xNode), &d)) return 1;
+        sd.nodes8x = (const float4*)d;
+        sd.light_root8x = (int32_t)ns8;
+        if (staged_upload(ctx, d, ns8, sizeof(Wide8xNode), 4096,
+                          [&](size_t f, size_t c, void* o) { std::memcpy(o, ctx->wide8x.nodes.data() + f, c * sizeof(Wide8xNode)); }))
+            return 1;
+        if (staged_upload(ctx, (char*)d + ns8 * sizeof(Wide8xNode), nl8, sizeof(Wide8xNode), 4096, [&](size_t f, size_t c, void* o) {
+                for (size_t i = 0; i < c; i++) {
+                    Wide8xNode w = ctx->lwide8x.nodes[f + i];
+                    for (int k = 0; k < 8; k++) {
+                        if (w.child[k] == WIDE_EMPTY) continue;
+                        if (w.child[k] >= 0) w.child[k] += (int32_t)ns8;
+                        else {
+                            const uint32_t code = (uint32_t)~w.child[k];
+                            w.child[k] = ~(int32_t)((((code >> 3) + (uint32_t)sc->n_triangles) << 3) | (code & 7u));
+                        }
+                    }
+                    ((Wide8xNode*)o)[i] = w;
+                }
+            }))
+            return 1;
     }
     ctx->use8 = ok8 && !ctx->quant;
     if (ctx->use8) {

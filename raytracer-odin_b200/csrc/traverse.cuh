@@ -96,7 +96,7 @@ struct TraceArgs {
 // QUANT selects the node encoding: WideNode (f32 planes, 7 x LDG.128 per visit) or QuantNode (8-bit
 // planes, 4 x LDG.128 per visit, ~35 % more ALU per visit).  Small scenes are issue bound and run
 // faster on WideNode; large scenes are bound by the L1/TEX pipe and run faster on QuantNode.
-template <bool CLOSEST, bool LIGHT, bool QUANT>
+template <bool CLOSEST, bool LIGHT, int QUANT>
 __global__ void __launch_bounds__(TRACE_THREADS, ORT_TRACE_MIN_CTAS)
 k_trace(const SceneDev s, const TraceArgs a) {
     __shared__ uint2 sh_stack[SMEM_STACK][TRACE_THREADS];
@@ -133,7 +133,7 @@ k_trace(const SceneDev s, const TraceArgs a) {
                     r = make_ray(ldg4(a.qo + idx), ldg4(a.qd + idx), s.pad_scale);
                     best = inf; hu = 0.0f; hv = 0.0f; htri = -1; lsumv = 0.0f; // max_dist = +inf (raytracer.odin:435)
                     cull = inf; sp = 0; pos = idx;
-                    if (!CLOSEST) { phase = 1; cur = s.light_root; }
+                    if (!CLOSEST) { phase = 1; cur = QUANT == 2 ? s.light_root8x : s.light_root; }
                     else { phase = 0; cur = 0; }
                 }
             }
@@ -145,6 +145,57 @@ k_trace(const SceneDev s, const TraceArgs a) {
         if (cur != WIDE_EMPTY) {
             for (;;) {
                 while (cur >= 0) {
+                    if (QUANT == 2) {
+                        // ---- exact-order 8-wide visit (Wide8xNode): eight slab tests, a 19-comparator sorting
+                        // network on (entry distance, child), far ... near pushed with their distances
+                        const float4* nd = s.nodes8x + (size_t)cur * 16;
+                        const int ox = (r.sx & 1) * 2, oy = (r.sy & 1) * 2, oz = (r.sz & 1) * 2;
+                        const F8 nxp = ldg8(nd + ox), fxp = ldg8(nd + (ox ^ 2));
+                        const F8 nyp = ldg8(nd + 4 + oy), fyp = ldg8(nd + 4 + (oy ^ 2));
+                        const F8 nzp = ldg8(nd + 8 + oz), fzp = ldg8(nd + 8 + (oz ^ 2));
+                        const F8 chf = ldg8(nd + 12);
+                        float e0, e1, e2, e3, e4, e5, e6, e7;
+                        int k0 = __float_as_int(chf.lo.x), k1 = __float_as_int(chf.lo.y), k2 = __float_as_int(chf.lo.z),
+                            k3 = __float_as_int(chf.lo.w), k4 = __float_as_int(chf.hi.x), k5 = __float_as_int(chf.hi.y),
+                            k6 = __float_as_int(chf.hi.z), k7 = __float_as_int(chf.hi.w);
+#define ORT_BOX8X(H, k, D)                                                                            \
+    {                                                                                                 \
+        const float tn = fmaxf(fmaxf(fmaf(nxp.H.k, r.ix, r.nx), fmaf(nyp.H.k, r.iy, r.ny)),           \
+                               fmaxf(fmaf(nzp.H.k, r.iz, r.nz), 0.0f));                               \
+        const float tf = fminf(fminf(fmaf(fxp.H.k, r.ix, r.fx), fmaf(fyp.H.k, r.iy, r.fy)),           \
+                               fminf(fmaf(fzp.H.k, r.iz, r.fz), cull));                               \
+        D = tn <= tf ? tn : inf;                                                                      \
+    }
+                        ORT_BOX8X(lo, x, e0) ORT_BOX8X(lo, y, e1) ORT_BOX8X(lo, z, e2) ORT_BOX8X(lo, w, e3)
+                        ORT_BOX8X(hi, x, e4) ORT_BOX8X(hi, y, e5) ORT_BOX8X(hi, z, e6) ORT_BOX8X(hi, w, e7)
+#undef ORT_BOX8X
+                        const int nh8 = (e0 < inf) + (e1 < inf) + (e2 < inf) + (e3 < inf) + (e4 < inf) + (e5 < inf) + (e6 < inf) + (e7 < inf);
+                        // Batcher odd-even merge sort, 19 comparators (misses carry +inf and sink to the end)
+                        ORT_CSWAP(e0, k0, e1, k1) ORT_CSWAP(e2, k2, e3, k3) ORT_CSWAP(e0, k0, e2, k2) ORT_CSWAP(e1, k1, e3, k3) ORT_CSWAP(e1, k1, e2, k2)
+                        ORT_CSWAP(e4, k4, e5, k5) ORT_CSWAP(e6, k6, e7, k7) ORT_CSWAP(e4, k4, e6, k6) ORT_CSWAP(e5, k5, e7, k7) ORT_CSWAP(e5, k5, e6, k6)
+                        ORT_CSWAP(e0, k0, e4, k4) ORT_CSWAP(e1, k1, e5, k5) ORT_CSWAP(e2, k2, e6, k6) ORT_CSWAP(e3, k3, e7, k7)
+                        ORT_CSWAP(e2, k2, e4, k4) ORT_CSWAP(e3, k3, e5, k5)
+                        ORT_CSWAP(e1, k1, e2, k2) ORT_CSWAP(e3, k3, e4, k4) ORT_CSWAP(e5, k5, e6, k6)
+                        if (nh8 == 0) {
+                            cur = WIDE_EMPTY;
+                            while (sp > 0) {
+                                int nd2; float dd;
+                                ORT_POP(nd2, dd)
+                                if (dd <= cull) { cur = nd2; break; }
+                            }
+                        } else {
+                            if (nh8 > 7) ORT_PUSH(k7, e7)
+                            if (nh8 > 6) ORT_PUSH(k6, e6)
+                            if (nh8 > 5) ORT_PUSH(k5, e5)
+                            if (nh8 > 4) ORT_PUSH(k4, e4)
+                            if (nh8 > 3) ORT_PUSH(k3, e3)
+                            if (nh8 > 2) ORT_PUSH(k2, e2)
+                            if (nh8 > 1) ORT_PUSH(k1, e1)
+                            cur = k0;
+                        }
+                        if (__popc(__activemask()) < a.inner_min) break;
+                        continue;
+                    }
                     float d0, d1, d2, d3;
                     int c0, c1, c2, c3;
                     if (!QUANT) {

@@ -99,6 +99,21 @@ struct alignas(32) Wide8Node {
 };
 static_assert(sizeof(Wide8Node) == 256, "Wide8Node must be two cache lines");
 
+// 8-wide node with explicit child references (same encoding as WideNode.child), for the exact-order
+// 8-wide traversal (k_trace<.., .., 2>): children sorted by entry distance at every visit, stack entries
+// carry their distance, leaves are stack entries — k_trace's algorithm on nodes twice as wide.
+struct alignas(32) Wide8xNode {
+    float bounds[3][2][8];
+    int32_t child[8];
+    int32_t pad[8];
+};
+static_assert(sizeof(Wide8xNode) == 256, "Wide8xNode must be two cache lines");
+struct Wide8xBVH {
+    std::vector<Wide8xNode> nodes; // root = 0
+    int depth = 0, max_stack = 0;
+};
+bool build_wide8x_bvh(const ort_bvh_node* bvh, int64_t n_nodes, int64_t n_tris, Wide8xBVH* out, const char** err);
+
 struct Wide8BVH {
     std::vector<Wide8Node> nodes;     // root = 0
     std::vector<uint32_t> tri_order;  // traversal-order position -> reference triangle index

@@ -434,9 +434,11 @@ def test_device_bvh_build_equals_oracle(scene_dir, orc):
 
 
 @pytest.mark.gpu
-def test_wide8_traversal_matches_default(scenes, monkeypatch):
-    """The opt-in 8-wide traversal (ORT_BVH8=1, traverse8.cuh) returns the same hits, bit for bit, as the
-    shipped 4-wide kernel on tie-free rays, and the same light-pdf sums to rounding."""
+@pytest.mark.parametrize("variant", ["1", "2"])
+def test_wide8_traversal_matches_default(scenes, monkeypatch, variant):
+    """The opt-in 8-wide traversals (ORT_BVH8=1: octant-ordered groups, traverse8.cuh; ORT_BVH8=2: exact order on
+    8-wide nodes, k_trace<.., .., 2>) return the same hits, bit for bit, as the shipped 4-wide kernel on tie-free
+    rays, and the same light-pdf sums to rounding."""
     from raytracer_odin_b200 import api
 
     for name in ("cornell", "spheres_small", "terrain_small"):
@@ -450,7 +452,7 @@ def test_wide8_traversal_matches_default(scenes, monkeypatch):
         rnd["d"] = (dd / np.linalg.norm(dd, axis=1, keepdims=True)).astype(np.float32)
         with api.Renderer(seed=5).upload_scene(s) as r4:
             t4, l4 = r4.trace_rays(rnd), r4.light_pdf(rnd)
-        monkeypatch.setenv("ORT_BVH8", "1")
+        monkeypatch.setenv("ORT_BVH8", variant)
         with api.Renderer(seed=5).upload_scene(s) as r8:
             h8 = r8.primary_hits(96, 64, sample=1)
             t8, l8 = r8.trace_rays(rnd), r8.light_pdf(rnd)
