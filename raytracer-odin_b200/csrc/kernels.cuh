@@ -27,7 +27,10 @@ constexpr float TAU_F = 6.28318530717958647692528676655900576f;
 #ifndef ORT_TRACE8_MIN_CTAS
 #define ORT_TRACE8_MIN_CTAS 1
 #endif
-constexpr int TRACE_THREADS = 128;
+#ifndef ORT_TRACE_THREADS
+#define ORT_TRACE_THREADS 128
+#endif
+constexpr int TRACE_THREADS = ORT_TRACE_THREADS;
 constexpr int SMEM_STACK = ORT_SMEM_STACK;        // stack entries per thread kept in shared memory
 constexpr int LOCAL_STACK = 128 - ORT_SMEM_STACK; // overflow entries per thread in local memory
 constexpr int MAX_STACK = SMEM_STACK + LOCAL_STACK;
