@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define ORT_ABI_VERSION 1
+#define ORT_ABI_VERSION 2
 
 /* ---- scene data handed over by the host (once per scene) --------------------------------- */
 
@@ -133,6 +133,8 @@ typedef struct ort_device_cfg {
     int32_t _pad;
     uint64_t seed;      /* key of the counter-based per-pixel RNG streams */
     int64_t max_paths_in_flight; /* 0 = default; path-state capacity of one wave */
+    int64_t max_path_bytes;      /* 0 = no limit; otherwise the library behaves as if only this much HBM were
+                                    free for path state (smaller waves, fewer pipelines, then an error) */
 } ort_device_cfg;
 
 typedef struct ort_stats {
@@ -152,6 +154,10 @@ typedef struct ort_stats {
     /* wide-BVH facts fixed at upload time */
     int64_t  wide_nodes, wide_depth, light_wide_nodes;
     int64_t  device_bytes;
+    int64_t  wide_max_stack;       /* exact worst-case stack occupancy of this library's traversal (never dropped) */
+    int64_t  reference_stack_need; /* worst-case occupancy of the REFERENCE's 64-entry stack on the same binary BVH
+                                      (2 * branch depth + 1, raytracer.odin:379,396-409): above 64 the reference
+                                      silently drops pushes and may miss hits this library finds */
 } ort_stats;
 
 typedef struct ort_ctx ort_ctx;
@@ -189,9 +195,11 @@ int  ort_render(ort_ctx* ctx, uint32_t w, uint32_t h, int32_t ray_depth,
                 ort_sample_stats* out, const volatile uint8_t* interrupt);
 
 /* Same render, device-resident: accumulates into a caller-owned DEVICE buffer of 8*w*h floats,
- * planar: total.r,g,b | total_squared.r,g,b | count (as float) | reserved, each plane w*h in
- * ort_sample_stats pixel order ((H-1-y)*W+x).  Asynchronous on the context stream.  This is the
- * buffer multi-GPU hosts reduce (one NCCL reduce per frame) before unpacking. */
+ * planar: total.r,g,b | total_squared.r,g,b | count_lo | count_hi, each plane w*h in
+ * ort_sample_stats pixel order ((H-1-y)*W+x); count = count_lo + 2^20 * count_hi, both exact integers
+ * in f32 (count_lo < 2^20 after every wave), so a float sum-reduce over the GPUs of a box keeps the u32
+ * count of Sample_Stats (main.odin:36) exact.  Asynchronous on the context stream.  This is the buffer
+ * multi-GPU hosts reduce (one NCCL reduce per frame) before unpacking. */
 int  ort_render_device(ort_ctx* ctx, uint32_t w, uint32_t h, int32_t ray_depth,
                        uint64_t first_sample, uint64_t n_samples, float* d_accum);
 
@@ -212,6 +220,55 @@ int  ort_light_pdf(ort_ctx* ctx, const ort_ray* rays, int64_t n, float* out);
 /* Tone-map on device: get_rgb_image (output.odin:30-80, mode Mean) from a planar device
  * accumulator to w*h*3 bytes (host). SURVEY §8(f) rank 2. */
 int  ort_tonemap_rgb8(ort_ctx* ctx, uint32_t w, uint32_t h, const float* d_accum, uint8_t* out_rgb);
+
+/* Samples per pixel the last ort_render / ort_render_device / ort_frame_render call of this context
+ * completed (== n_samples unless `interrupt` fired between waves, raytracer.odin:554). */
+uint64_t ort_last_render_samples(const ort_ctx* ctx);
+
+/* ---- device-resident frame (--continious, main.odin:207; live preview, debug.odin:80) ----------
+ * ort_render moves 52 bytes per pixel to the host on every call.  A frame keeps the accumulators
+ * (total, total_squared, count, first, last) in HBM across calls:
+ *   ort_frame_begin   allocates and clears them for a w x h image (discarding a previous frame);
+ *   ort_frame_load    (optional) seeds them from host Sample_Stats, e.g. a resumed checkpoint;
+ *   ort_frame_render  enqueues samples [first_sample, first_sample + n_samples) and returns without
+ *                     waiting for the device (with `interrupt` it stays a few waves ahead at most and
+ *                     stops enqueuing once the flag is set); *done (may be NULL) = samples enqueued;
+ *   ort_frame_wait    blocks until everything enqueued has been rendered;
+ *   ort_frame_snapshot  copies the accumulators, as of everything enqueued so far, into the frame's second
+ *                     buffer (device to device, asynchronous): samples enqueued AFTER it render while the
+ *                     snapshot is tone-mapped and read back;
+ *   ort_frame_preview_rgb8  get_rgb_image (output.odin:30-80) of the pending snapshot (takes one if there
+ *                     is none) on the device, 3 bytes per pixel to the host; waits for the snapshot only;
+ *   ort_frame_fetch   OVERWRITES `out` with the frame's Sample_Stats (52 bytes per pixel) — once, at
+ *                     exit or at a checkpoint;
+ *   ort_frame_end     releases the frame. */
+int  ort_frame_begin(ort_ctx* ctx, uint32_t w, uint32_t h);
+int  ort_frame_load(ort_ctx* ctx, const ort_sample_stats* in);
+int  ort_frame_render(ort_ctx* ctx, int32_t ray_depth, uint64_t first_sample, uint64_t n_samples,
+                      const volatile uint8_t* interrupt, uint64_t* done);
+int  ort_frame_wait(ort_ctx* ctx);
+int  ort_frame_snapshot(ort_ctx* ctx);
+int  ort_frame_preview_rgb8(ort_ctx* ctx, uint8_t* out_rgb);
+int  ort_frame_fetch(ort_ctx* ctx, ort_sample_stats* out);
+int  ort_frame_end(ort_ctx* ctx);
+
+/* Parity probe for the shading device functions: runs n independent evaluations of the SAME __device__
+ * functions k_shade calls, one per thread.  `in` / `out` are n records of the floats listed below
+ * (u32 values are passed as their bit patterns).  Kinds that need scene data (lights, textures,
+ * environment map) use the uploaded scene.
+ *   ORT_PROBE_SHADE        in: n[3] color[3] metallic roughness in_d[3] out_d[3]   out: value[3]    shade, shading.odin:164-204
+ *   ORT_PROBE_VNDF_SAMPLE  in: n[3] omega[3] alpha u1 u2                             out: h[3]        vndf_sampling, shading.odin:102-122
+ *   ORT_PROBE_VNDF_PDF     in: n[3] omega[3] alpha L[3]                              out: pdf         vndf_sampling_pdf, shading.odin:124-137
+ *   ORT_PROBE_SAMPLE       in: n[3] pos[3] roughness in_d[3] r[4](u32)               out: dir[3]      sample, shading.odin:139-151
+ *   ORT_PROBE_PDF          in: n[3] pos[3] roughness in_d[3] out_d[3]                out: pdf         pdf, shading.odin:153-162 (incl. the light-BVH sum)
+ *   ORT_PROBE_TEXTURE      in: texture(i32 bits; -1 = environment map) srgb u v      out: rgba[4]     texture_sample, textures.odin:79-135
+ *   ORT_PROBE_COSINE       in: n[3] r1(u32) r2(u32)                                  out: dir[3] pdf  cosine_weighted(_pdf), shading.odin:17-39
+ *   ORT_PROBE_ENV          in: d[3]                                                  out: rgb[3]      environment lookup, raytracer.odin:437-446 */
+enum {
+    ORT_PROBE_SHADE = 0, ORT_PROBE_VNDF_SAMPLE = 1, ORT_PROBE_VNDF_PDF = 2, ORT_PROBE_SAMPLE = 3,
+    ORT_PROBE_PDF = 4, ORT_PROBE_TEXTURE = 5, ORT_PROBE_COSINE = 6, ORT_PROBE_ENV = 7
+};
+int  ort_probe_shading(ort_ctx* ctx, int32_t kind, const float* in, int64_t n, float* out);
 
 /* Diagnostic: time the traversal kernel alone.  Uploads n host rays once, launches the closest-hit
  * (mode 0) or light-sum (mode 1) kernel `iters` times over them and returns the mean device time of
@@ -246,6 +303,22 @@ int  ort_multi_render(ort_multi* m, uint32_t w, uint32_t h, int32_t ray_depth,
                       uint64_t first_sample, uint64_t n_samples,
                       ort_sample_stats* out, const volatile uint8_t* interrupt);
 int  ort_multi_get_stats(ort_multi* m, ort_stats* out); /* counters summed, times = max over devices */
+/* Samples per pixel the last ort_multi_render / ort_multi_frame_render completed, summed over the GPUs
+ * (== n_samples unless interrupted; an interrupted call still consumes its whole index range, so no
+ * sample index is ever rendered twice). */
+uint64_t ort_multi_last_render_samples(const ort_multi* m);
+/* Device-resident frame on several GPUs: every GPU keeps its own accumulators and renders its block of
+ * each ort_multi_frame_render call; preview / fetch snapshot them on every GPU, and devices[0] sums the
+ * snapshots through NVLink peer memory on a side stream WHILE the next samples render. */
+int  ort_multi_frame_begin(ort_multi* m, uint32_t w, uint32_t h);
+int  ort_multi_frame_load(ort_multi* m, const ort_sample_stats* in);
+int  ort_multi_frame_render(ort_multi* m, int32_t ray_depth, uint64_t first_sample, uint64_t n_samples,
+                            const volatile uint8_t* interrupt, uint64_t* done);
+int  ort_multi_frame_wait(ort_multi* m);
+int  ort_multi_frame_snapshot(ort_multi* m);
+int  ort_multi_frame_preview_rgb8(ort_multi* m, uint8_t* out_rgb);
+int  ort_multi_frame_fetch(ort_multi* m, ort_sample_stats* out);
+int  ort_multi_frame_end(ort_multi* m);
 
 /* Host-side scene finalisation helper (NOT used when Odin is the host): the reference
  * bvh_build (raytracer.odin:227-342) as native code, for hosts that do not have one.

@@ -24,10 +24,11 @@ class OrtError(RuntimeError):
 
 
 class Renderer:
-    def __init__(self, device: int = 0, seed: int = 0, max_paths_in_flight: int = 0):
+    def __init__(self, device: int = 0, seed: int = 0, max_paths_in_flight: int = 0, max_path_bytes: int = 0):
         self.lib = cabi.load_library()
         self._ctx = C.c_void_p()
-        cfg = cabi.OrtDeviceCfg(device=device, seed=seed, max_paths_in_flight=max_paths_in_flight)
+        cfg = cabi.OrtDeviceCfg(device=device, seed=seed, max_paths_in_flight=max_paths_in_flight,
+                                max_path_bytes=max_path_bytes)
         if self.lib.ort_create(C.byref(self._ctx), C.byref(cfg)) != 0:
             raise OrtError(self.lib.ort_last_error(None).decode())
         self.device = device
@@ -125,7 +126,58 @@ class Renderer:
         self._check(self.lib.ort_tonemap_rgb8(self._ctx, width, height, C.c_void_p(d_accum_ptr), cabi.ptr(out)))
         return out
 
+    def last_render_samples(self) -> int:
+        return int(self.lib.ort_last_render_samples(self._ctx))
+
+    # -- device-resident frame (--continious / live preview): accumulators stay in HBM across calls --------
+    def frame_begin(self, width: int, height: int):
+        self._check(self.lib.ort_frame_begin(self._ctx, width, height))
+        self._frame = (width, height)
+        return self
+
+    def frame_load(self, pixels: np.ndarray):
+        pixels = np.ascontiguousarray(pixels, cabi.STATS_DTYPE)
+        assert pixels.size == self._frame[0] * self._frame[1]
+        self._check(self.lib.ort_frame_load(self._ctx, cabi.ptr(pixels)))
+
+    def frame_render(self, ray_depth: int, first_sample: int, n_samples: int, interrupt: Optional[np.ndarray] = None) -> int:
+        """Enqueue samples [first_sample, first_sample + n_samples); returns the number enqueued."""
+        done = C.c_uint64()
+        iptr = interrupt.ctypes.data_as(C.c_void_p) if interrupt is not None else None
+        self._check(self.lib.ort_frame_render(self._ctx, ray_depth, first_sample, n_samples, iptr, C.byref(done)))
+        return int(done.value)
+
+    def frame_wait(self):
+        self._check(self.lib.ort_frame_wait(self._ctx))
+
+    def frame_snapshot(self):
+        self._check(self.lib.ort_frame_snapshot(self._ctx))
+
+    def frame_preview_rgb8(self) -> np.ndarray:
+        w, h = self._frame
+        out = np.zeros((h, w, 3), np.uint8)
+        self._check(self.lib.ort_frame_preview_rgb8(self._ctx, cabi.ptr(out)))
+        return out
+
+    def frame_fetch(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        w, h = self._frame
+        if out is None:
+            out = np.zeros(w * h, cabi.STATS_DTYPE)
+        self._check(self.lib.ort_frame_fetch(self._ctx, cabi.ptr(out)))
+        return out
+
+    def frame_end(self):
+        self._check(self.lib.ort_frame_end(self._ctx))
+
     # -- parity probes -------------------------------------------------------------------------
+    def probe_shading(self, kind: str, records: np.ndarray) -> np.ndarray:
+        """n evaluations of a shading device function (cabi.PROBE); u32 inputs are passed as bit patterns."""
+        code, ni, no = cabi.PROBE[kind]
+        rec = np.ascontiguousarray(records, np.float32).reshape(-1, ni)
+        out = np.zeros((len(rec), no), np.float32)
+        self._check(self.lib.ort_probe_shading(self._ctx, code, cabi.ptr(rec), len(rec), cabi.ptr(out)))
+        return out
+
     def trace_rays(self, rays: np.ndarray) -> np.ndarray:
         rays = np.ascontiguousarray(rays, cabi.RAY_DTYPE)
         out = np.zeros(len(rays), cabi.HIT_DTYPE)
@@ -218,6 +270,47 @@ class MultiRenderer:
         s = cabi.OrtStats()
         self._check(self.lib.ort_multi_get_stats(self._m, C.byref(s)))
         return s.as_dict()
+
+    def last_render_samples(self) -> int:
+        return int(self.lib.ort_multi_last_render_samples(self._m))
+
+    # -- device-resident frame on all GPUs --------------------------------------------------------
+    def frame_begin(self, width: int, height: int):
+        self._check(self.lib.ort_multi_frame_begin(self._m, width, height))
+        self._frame = (width, height)
+        return self
+
+    def frame_load(self, pixels: np.ndarray):
+        pixels = np.ascontiguousarray(pixels, cabi.STATS_DTYPE)
+        self._check(self.lib.ort_multi_frame_load(self._m, cabi.ptr(pixels)))
+
+    def frame_render(self, ray_depth: int, first_sample: int, n_samples: int, interrupt=None) -> int:
+        done = C.c_uint64()
+        iptr = interrupt.ctypes.data_as(C.c_void_p) if interrupt is not None else None
+        self._check(self.lib.ort_multi_frame_render(self._m, ray_depth, first_sample, n_samples, iptr, C.byref(done)))
+        return int(done.value)
+
+    def frame_wait(self):
+        self._check(self.lib.ort_multi_frame_wait(self._m))
+
+    def frame_snapshot(self):
+        self._check(self.lib.ort_multi_frame_snapshot(self._m))
+
+    def frame_preview_rgb8(self) -> np.ndarray:
+        w, h = self._frame
+        out = np.zeros((h, w, 3), np.uint8)
+        self._check(self.lib.ort_multi_frame_preview_rgb8(self._m, cabi.ptr(out)))
+        return out
+
+    def frame_fetch(self, out=None) -> np.ndarray:
+        w, h = self._frame
+        if out is None:
+            out = np.zeros(w * h, cabi.STATS_DTYPE)
+        self._check(self.lib.ort_multi_frame_fetch(self._m, cabi.ptr(out)))
+        return out
+
+    def frame_end(self):
+        self._check(self.lib.ort_multi_frame_end(self._m))
 
 
 CKPT_MAGIC = b"ORTCKPT1"

@@ -75,7 +75,8 @@ class OrtScene(C.Structure):
 
 
 class OrtDeviceCfg(C.Structure):
-    _fields_ = [("device", C.c_int32), ("_pad", C.c_int32), ("seed", C.c_uint64), ("max_paths_in_flight", C.c_int64)]
+    _fields_ = [("device", C.c_int32), ("_pad", C.c_int32), ("seed", C.c_uint64), ("max_paths_in_flight", C.c_int64),
+                ("max_path_bytes", C.c_int64)]
 
 
 class OrtStats(C.Structure):
@@ -85,7 +86,7 @@ class OrtStats(C.Structure):
         ("render_ms", C.c_double), ("trace_ms", C.c_double), ("light_ms", C.c_double),
         ("shade_ms", C.c_double), ("other_ms", C.c_double),
         ("wide_nodes", C.c_int64), ("wide_depth", C.c_int64), ("light_wide_nodes", C.c_int64),
-        ("device_bytes", C.c_int64),
+        ("device_bytes", C.c_int64), ("wide_max_stack", C.c_int64), ("reference_stack_need", C.c_int64),
     ]
 
     def as_dict(self):
@@ -123,7 +124,30 @@ ABI = {
     "ort_multi_upload_scene": (C.c_int, [C.c_void_p, C.POINTER(OrtScene)]),
     "ort_multi_render": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int32, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]),
     "ort_multi_get_stats": (C.c_int, [C.c_void_p, C.POINTER(OrtStats)]),
+    "ort_last_render_samples": (C.c_uint64, [C.c_void_p]),
+    "ort_frame_begin": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
+    "ort_frame_load": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ort_frame_render": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint64, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64)]),
+    "ort_frame_wait": (C.c_int, [C.c_void_p]),
+    "ort_frame_snapshot": (C.c_int, [C.c_void_p]),
+    "ort_frame_preview_rgb8": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ort_frame_fetch": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ort_frame_end": (C.c_int, [C.c_void_p]),
+    "ort_probe_shading": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
+    "ort_multi_last_render_samples": (C.c_uint64, [C.c_void_p]),
+    "ort_multi_frame_begin": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
+    "ort_multi_frame_load": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ort_multi_frame_render": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint64, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64)]),
+    "ort_multi_frame_wait": (C.c_int, [C.c_void_p]),
+    "ort_multi_frame_snapshot": (C.c_int, [C.c_void_p]),
+    "ort_multi_frame_preview_rgb8": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ort_multi_frame_fetch": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ort_multi_frame_end": (C.c_int, [C.c_void_p]),
 }
+
+# ort_probe_shading: kind -> (floats in, floats out) per record (include/odinrt_b200.h)
+PROBE = {"shade": (0, 14, 3), "vndf_sample": (1, 9, 3), "vndf_pdf": (2, 10, 1), "sample": (3, 14, 3), "pdf": (4, 13, 1),
+         "texture": (5, 4, 4), "cosine": (6, 5, 4), "env": (7, 3, 3)}
 
 _lib = None
 
@@ -145,7 +169,7 @@ def load_library(path=None):
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.ort_abi_version() != 1:
+    if lib.ort_abi_version() != 2:
         raise RuntimeError("libodinrt_b200.so ABI version mismatch")
     if path is None:
         _lib = lib

@@ -53,28 +53,34 @@ def main(argv=None):
     r = (api.Renderer(device=devices[0], seed=a.seed) if len(devices) == 1
          else api.MultiRenderer(devices, seed=a.seed)).upload_scene(scene)
     w, h = a.width, a.height
-    pixels, resume_at = np.zeros(w * h, cabi.STATS_DTYPE), 0
+    # the frame: accumulators stay in HBM for the whole run (ort_frame_*), like host/main.cpp
+    r.frame_begin(w, h)
+    resume_at = 0
     if a.resume:  # raw accumulators + the next sample index: the counter-based streams continue seamlessly
         pixels, resume_at = api.load_checkpoint(a.resume, w, h)
-    if a.continious:  # samples = max(int): render waves until interrupted (main.odin:207)
-        first, chunk = resume_at, 16
+        r.frame_load(pixels)
+    if a.continious:  # samples = max(int): render chunks until interrupted (main.odin:207)
+        first, chunk, rendered = resume_at, 64 * len(devices), 0
         t0 = time.perf_counter()
         while not interrupt[0]:
-            r.render(w, h, a.ray_depth, chunk, first, pixels, interrupt)
+            rendered += r.frame_render(a.ray_depth, first, chunk, interrupt)
             first += chunk
-        print(f"Rendered {first} samples in {time.perf_counter() - t0:.2f}s")
+        r.frame_wait()
+        print(f"Rendered {rendered} samples in {time.perf_counter() - t0:.2f}s")
     else:
         trials = a.times if a.times > 0 else 1
         timings = []
         for trial in range(trials):
             t0 = time.perf_counter()
-            r.render(w, h, a.ray_depth, a.num_samples, resume_at, pixels, interrupt)
+            r.frame_render(a.ray_depth, resume_at, a.num_samples, interrupt)
+            r.frame_wait()
             timings.append(time.perf_counter() - t0)
             print(f"Trial {trial} >>> Rendered in {timings[-1] * 1e3:.3f}ms")
         first = resume_at + a.num_samples
         st = r.stats()
         total = sum(timings)
         print(f"{st['rays_closest'] / total / 1e6:.1f} Mrays/s, {st['paths'] / total / 1e6:.1f} Msamples/s")
+    pixels = r.frame_fetch()  # the one 52-byte-per-pixel transfer of the run
     if a.checkpoint:
         api.save_checkpoint(a.checkpoint, pixels, first, w, h)
     if a.output_file:

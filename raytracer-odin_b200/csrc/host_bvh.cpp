@@ -60,7 +60,7 @@ struct Build {
     Ent* ent;
     Ent* tmp;
     Box* suffix;
-    bool failed = false;
+    std::atomic<bool> failed{false};
 
     // Stable ascending sort of ent[b, b+n) by box.lo[axis].
     void sort_axis(int64_t b, int64_t n, int axis) {
@@ -285,9 +285,11 @@ bool build_wide_bvh(const ort_bvh_node* bvh, int64_t n_nodes, int64_t n_tris, Wi
                 size_t inner = 0;
                 for (int k = 0; k < it.nk; k++) {
                     const ort_bvh_node& ch = bvh[it.kids[k]];
+                    // empty leaf (only a host-supplied BVH can hold one below the root): the slot stays unused AND
+                    // keeps its inverted infinite box — the kernels rely on the box alone to skip unused slots
+                    if (ch.kind == 0 && ch.b == 0) continue;
                     for (int ax = 0; ax < 3; ax++) { wn.bounds[ax][0][k] = ch.lo[ax]; wn.bounds[ax][1][k] = ch.hi[ax]; }
                     if (ch.kind == 0) {
-                        if (ch.b == 0) continue; // empty leaf: leave the slot unused
                         wn.child[k] = ~(int32_t)((ch.a << 3) | ch.b);
                     } else {
                         const size_t pos = it.child_off + inner++;
@@ -318,233 +320,16 @@ bool build_wide_bvh(const ort_bvh_node* bvh, int64_t n_nodes, int64_t n_tris, Wi
     return true;
 }
 
-bool build_wide8x_bvh(const ort_bvh_node* bvh, int64_t n_nodes, int64_t n_tris, Wide8xBVH* out, const char** err) {
-    out->nodes.clear();
-    out->depth = 0;
-    out->max_stack = 0;
-    if (n_nodes <= 0) { *err = "empty BVH node array"; return false; }
-    struct Pending { int64_t src; int32_t dst; int level; };
-    std::vector<Pending> queue;
-    out->nodes.emplace_back();
-    queue.push_back({n_nodes - 1, 0, 1});
-    auto area = [&](int64_t id) {
-        const ort_bvh_node& nd = bvh[id];
-        float sx = nd.hi[0] - nd.lo[0], sy = nd.hi[1] - nd.lo[1], sz = nd.hi[2] - nd.lo[2];
-        float a = sx * sy + sy * sz + sz * sx;
-        return std::isfinite(a) ? a : 0.0f;
-    };
-    for (size_t qi = 0; qi < queue.size(); qi++) {
-        const Pending cur = queue[qi];
-        if (cur.level > out->depth) out->depth = cur.level;
-        int64_t kids[8];
-        int nk = 0;
-        if (bvh[cur.src].kind == 0) {
-            if (bvh[cur.src].b > 0) kids[nk++] = cur.src;
-        } else {
-            kids[nk++] = bvh[cur.src].a;
-            kids[nk++] = bvh[cur.src].b;
-            while (nk < 8) {
-                int pick = -1;
-                float best = -1.0f;
-                for (int i = 0; i < nk; i++)
-                    if (bvh[kids[i]].kind == 1 && area(kids[i]) > best) { best = area(kids[i]); pick = i; }
-                if (pick < 0) break;
-                const int64_t open = kids[pick];
-                kids[pick] = bvh[open].a;
-                kids[nk++] = bvh[open].b;
-            }
-        }
-        Wide8xNode wn;
-        std::memset(&wn, 0, sizeof wn);
-        for (int k = 0; k < 8; k++) {
-            for (int ax = 0; ax < 3; ax++) { wn.bounds[ax][0][k] = kInf; wn.bounds[ax][1][k] = -kInf; }
-            wn.child[k] = WIDE_EMPTY;
-        }
-        for (int k = 0; k < nk; k++) {
-            const ort_bvh_node& c = bvh[kids[k]];
-            for (int ax = 0; ax < 3; ax++) { wn.bounds[ax][0][k] = c.lo[ax]; wn.bounds[ax][1][k] = c.hi[ax]; }
-            if (c.kind == 0) {
-                if (c.a < 0 || c.b < 0 || c.b > 7 || c.a + c.b > n_tris) { *err = "BVH leaf out of range (first/count)"; return false; }
-                if (c.b == 0) continue;
-                wn.child[k] = ~(int32_t)((c.a << 3) | c.b);
-            } else {
-                if (out->nodes.size() >= (size_t)0x7fffffff) { *err = "wide BVH too large"; return false; }
-                wn.child[k] = (int32_t)out->nodes.size();
-                out->nodes.emplace_back();
-                queue.push_back({kids[k], wn.child[k], cur.level + 1});
-            }
-        }
-        out->nodes[cur.dst] = wn;
+int64_t reference_stack_need(const ort_bvh_node* bvh, int64_t n_nodes) {
+    if (n_nodes <= 0) return 0;
+    // post-order array: children precede their parent (validated by build_wide_bvh)
+    std::vector<int32_t> branches((size_t)n_nodes, 0);
+    for (int64_t i = 0; i < n_nodes; i++) {
+        const ort_bvh_node& nd = bvh[i];
+        if (nd.kind == 1 && nd.a >= 0 && nd.b >= 0 && nd.a < i && nd.b < i)
+            branches[(size_t)i] = 1 + std::max(branches[(size_t)nd.a], branches[(size_t)nd.b]);
     }
-    std::vector<int> need(out->nodes.size(), 0);
-    for (int64_t i = (int64_t)out->nodes.size() - 1; i >= 0; i--) {
-        int c = 0, deepest = 0;
-        for (int k = 0; k < 8; k++) {
-            const int32_t ch = out->nodes[i].child[k];
-            if (ch == WIDE_EMPTY) continue;
-            c++;
-            if (ch >= 0 && need[ch] > deepest) deepest = need[ch];
-        }
-        need[i] = (c > 0 ? c - 1 : 0) + deepest;
-    }
-    out->max_stack = need[0] + 1;
-    return true;
-}
-
-bool build_wide8_bvh(const ort_bvh_node* bvh, int64_t n_nodes, int64_t n_tris, Wide8BVH* out, const char** err) {
-    out->nodes.clear();
-    out->tri_order.clear();
-    out->depth = 0;
-    if (n_nodes <= 0) { *err = "empty BVH node array"; return false; }
-    out->tri_order.reserve((size_t)n_tris);
-    struct Pending { int64_t src; uint32_t dst; int level; };
-    std::vector<Pending> queue;
-    out->nodes.emplace_back();
-    queue.push_back({n_nodes - 1, 0u, 1});
-    auto area = [&](int64_t id) {
-        const ort_bvh_node& nd = bvh[id];
-        float sx = nd.hi[0] - nd.lo[0], sy = nd.hi[1] - nd.lo[1], sz = nd.hi[2] - nd.lo[2];
-        float a = sx * sy + sy * sz + sz * sx;
-        return std::isfinite(a) ? a : 0.0f;
-    };
-    for (size_t qi = 0; qi < queue.size(); qi++) {
-        const Pending cur = queue[qi];
-        if (cur.level > out->depth) out->depth = cur.level;
-        int64_t kids[8];
-        int nk = 0;
-        if (bvh[cur.src].kind == 0) {
-            if (bvh[cur.src].b > 0) kids[nk++] = cur.src; // a lone (root) leaf
-        } else {
-            kids[nk++] = bvh[cur.src].a;
-            kids[nk++] = bvh[cur.src].b;
-            while (nk < 8) { // open the largest inner child until the node is full
-                int pick = -1;
-                float best = -1.0f;
-                for (int i = 0; i < nk; i++)
-                    if (bvh[kids[i]].kind == 1 && area(kids[i]) > best) { best = area(kids[i]); pick = i; }
-                if (pick < 0) break;
-                const int64_t open = kids[pick];
-                kids[pick] = bvh[open].a;
-                kids[nk++] = bvh[open].b;
-            }
-        }
-        // slot assignment: greedy maximum of dot(child centre - node centre, slot direction)
-        int slot_of[8], kid_at[8];
-        for (int i = 0; i < 8; i++) { slot_of[i] = -1; kid_at[i] = -1; }
-        {
-            const ort_bvh_node& pn = bvh[cur.src];
-            float pc[3], cost[8][8];
-            for (int ax = 0; ax < 3; ax++) pc[ax] = 0.5f * (pn.lo[ax] + pn.hi[ax]);
-            for (int i = 0; i < nk; i++) {
-                const ort_bvh_node& c = bvh[kids[i]];
-                float d[3];
-                for (int ax = 0; ax < 3; ax++) {
-                    d[ax] = 0.5f * (c.lo[ax] + c.hi[ax]) - pc[ax];
-                    if (!std::isfinite(d[ax])) d[ax] = 0.0f;
-                }
-                for (int sl = 0; sl < 8; sl++)
-                    cost[i][sl] = ((sl & 1) ? d[0] : -d[0]) + ((sl & 2) ? d[1] : -d[1]) + ((sl & 4) ? d[2] : -d[2]);
-            }
-            for (int round = 0; round < nk; round++) {
-                int bi = -1, bs = -1;
-                float bc = -kInf;
-                for (int i = 0; i < nk; i++) {
-                    if (slot_of[i] >= 0) continue;
-                    for (int sl = 0; sl < 8; sl++)
-                        if (kid_at[sl] < 0 && cost[i][sl] > bc) { bc = cost[i][sl]; bi = i; bs = sl; }
-                }
-                slot_of[bi] = bs;
-                kid_at[bs] = bi;
-            }
-        }
-        Wide8Node wn;
-        std::memset(&wn, 0, sizeof wn);
-        for (int sl = 0; sl < 8; sl++)
-            for (int ax = 0; ax < 3; ax++) { wn.bounds[ax][0][sl] = kInf; wn.bounds[ax][1][sl] = -kInf; }
-        wn.child_base = (uint32_t)out->nodes.size();
-        wn.tri_base = (uint32_t)out->tri_order.size();
-        uint32_t tri_off = 0;
-        for (int sl = 0; sl < 8; sl++) {
-            if (kid_at[sl] < 0) continue;
-            const ort_bvh_node& c = bvh[kids[kid_at[sl]]];
-            if (c.kind == 0 && c.b == 0) continue; // empty leaf: slot stays unused
-            for (int ax = 0; ax < 3; ax++) { wn.bounds[ax][0][sl] = c.lo[ax]; wn.bounds[ax][1][sl] = c.hi[ax]; }
-            if (c.kind == 0) {
-                if (c.a < 0 || c.b < 0 || c.a + c.b > n_tris) { *err = "BVH leaf out of range (first/count)"; return false; }
-                if (tri_off + (uint32_t)c.b > 32u) { *err = "8-wide node would reference more than 32 triangles"; return false; }
-                wn.trimask[sl] = (uint32_t)((((uint64_t)1 << c.b) - 1) << tri_off);
-                for (int64_t t = 0; t < c.b; t++) out->tri_order.push_back((uint32_t)(c.a + t));
-                tri_off += (uint32_t)c.b;
-            } else {
-                if (out->nodes.size() >= (size_t)0x7fffffff) { *err = "wide BVH too large"; return false; }
-                wn.imask |= 1u << sl;
-                const uint32_t dst = (uint32_t)out->nodes.size();
-                out->nodes.emplace_back();
-                queue.push_back({kids[kid_at[sl]], dst, cur.level + 1});
-            }
-        }
-        out->nodes[cur.dst] = wn;
-    }
-    return true;
-}
-
-void quantize_wide_nodes(const WideNode* in, size_t n, QuantNode* out) {
-    for (size_t i = 0; i < n; i++) {
-        const WideNode& w = in[i];
-        QuantNode q;
-        std::memset(&q, 0, sizeof q);
-        for (int k = 0; k < 4; k++) q.child[k] = w.child[k];
-        for (int ax = 0; ax < 3; ax++) {
-            double lo = std::numeric_limits<double>::infinity(), hi = -lo;
-            for (int k = 0; k < 4; k++) {
-                if (w.child[k] == WIDE_EMPTY) continue;
-                lo = std::min(lo, (double)w.bounds[ax][0][k]);
-                hi = std::max(hi, (double)w.bounds[ax][1][k]);
-            }
-            if (!(lo <= hi) || !std::isfinite(lo) || !std::isfinite(hi)) { lo = 0; hi = 0; } // no children / non-finite
-            // smallest power-of-two step with 250 steps >= extent (headroom for the slack and for
-            // moving the origin one step below the lowest plane, so that plane keeps its slack too)
-            int e = 1;
-            const double extent = hi - lo;
-            if (extent > 0) {
-                int ex;
-                std::frexp(extent / 250.0, &ex); // extent/250 = m * 2^ex, m in [0.5, 1)  ->  2^ex >= extent/250
-                e = ex + 127;
-            }
-            e = std::max(1, std::min(e, 254 - 15)); // the kernel multiplies the step by 2^15
-            float origin = 0.0f;
-            for (;;) {
-                const double step = std::ldexp(1.0, e - 127);
-                const double slack = step / 128.0; // covers the kernel's decode rounding (2^-9 step) generously
-                origin = (float)(lo - step);
-                if ((double)origin > lo - step) origin = std::nextafterf(origin, -std::numeric_limits<float>::infinity());
-                if (!std::isfinite(origin)) origin = (float)lo;
-                bool ok = true;
-                uint32_t wlo = 0, whi = 0;
-                for (int k = 0; k < 4; k++) {
-                    uint32_t ql = 255, qh = 0; // unused slot: inverted, never hit (and flagged by child)
-                    if (w.child[k] != WIDE_EMPTY) {
-                        double a = std::floor(((double)w.bounds[ax][0][k] - slack - origin) / step);
-                        double b = std::ceil(((double)w.bounds[ax][1][k] + slack - origin) / step);
-                        if (!(a == a)) a = 0;   // NaN inputs: keep the node harmless
-                        if (!(b == b)) b = 255;
-                        if (a < 0) a = 0;
-                        if (b > 255) { ok = false; break; }
-                        ql = (uint32_t)a; qh = (uint32_t)b;
-                    }
-                    wlo |= ql << (8 * k);
-                    whi |= qh << (8 * k);
-                }
-                if (ok) { q.planes[ax][0] = wlo; q.planes[ax][1] = whi; break; }
-                if (++e > 254 - 15) { // cannot happen for finite input; degrade to "everything"
-                    q.planes[ax][0] = 0; q.planes[ax][1] = 0xffffffffu; e = 254 - 15; break;
-                }
-            }
-            q.origin[ax] = origin;
-            q.exps |= (uint32_t)e << (8 * ax);
-        }
-        out[i] = q;
-    }
+    return 2 * (int64_t)branches[(size_t)n_nodes - 1] + 1;
 }
 
 void make_isect_records(const ort_triangle* tris, int64_t n, TriIsect* out) {

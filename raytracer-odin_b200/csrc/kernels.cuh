@@ -2,8 +2,8 @@
 //
 //   k_raygen      render_task's inner loop head (raytracer.odin:580-586): jittered pinhole rays
 //   k_trace       (traverse.cuh) cast_ray (raytracer.odin:416-430) on the 4-wide re-emission of the
-//                 reference BVH fused with surface_sampling_pdf_bvh_sum (shading.odin:62-94) on the
-//                 light BVH: persistent warps, phase voting, per-lane dynamic fetch
+//                 reference BVH, and surface_sampling_pdf_bvh_sum (shading.odin:62-94) on the light
+//                 BVH: persistent warps, per-lane dynamic fetch
 //   k_shade       raytrace's body (raytracer.odin:437-500) + sample/pdf/shade (shading.odin),
 //                 texture fetches through texture objects, ballot/prefix-sum queue compaction
 //   k_resolve     rc_set_pixel (main.odin:89-102): per-pixel accumulation in sample order
@@ -23,9 +23,6 @@ constexpr float TAU_F = 6.28318530717958647692528676655900576f;
 #endif
 #ifndef ORT_TRACE_MIN_CTAS
 #define ORT_TRACE_MIN_CTAS 1
-#endif
-#ifndef ORT_TRACE8_MIN_CTAS
-#define ORT_TRACE8_MIN_CTAS 1
 #endif
 #ifndef ORT_TRACE_THREADS
 #define ORT_TRACE_THREADS 128
@@ -63,14 +60,6 @@ struct SceneDev {
     int32_t has_env;
     int32_t n_lights;
     float pad_scale[3];  // max |coordinate| of the scene root box (light triangles are scene triangles)
-    // 8-wide re-emission (traverse8.cuh): Wide8Node[], 16 float4 each, scene tree (root 0) then light tree;
-    // TriIsect[] in TRAVERSAL order (pad[0] = reference triangle index), scene then light triangles
-    const float4* nodes8;
-    const float4* tris8;
-    int32_t light_root8;
-    // exact-order 8-wide re-emission (Wide8xNode[], child references like WideNode; k_trace<.., .., 2>)
-    const float4* nodes8x;
-    int32_t light_root8x;
 };
 
 struct RenderParams {
@@ -168,7 +157,6 @@ __device__ __forceinline__ bool tri_uv(const RaySetup& r, float4 a, float4 b, fl
 
 } // namespace ort
 #include "traverse.cuh"
-#include "traverse8.cuh"
 namespace ort {
 
 // ------------------------------------------------------------------------------------------------
@@ -353,6 +341,50 @@ __device__ f3 brdf_cos(f3 color, f3 N, float metallic, float roughness, f3 in_d,
     return diel * (1.0f - metallic) + met * metallic;
 }
 
+// sphere_uniform + n, normalised (cosine_weighted, shading.odin:9-15,32-35)
+__device__ __forceinline__ f3 cosine_weighted(f3 N, uint32_t r1, uint32_t r2) {
+    const float phi = u01(r1) * (TAU_F - 0.0f) + 0.0f;
+    const float z = u01(r2) * (1.0f - -1.0f) + -1.0f;
+    float sx, sy;
+    sincosf(phi, &sx, &sy);
+    const float radius = sqrtf(1.0f - sq(z));
+    return normalize3(mk3(sx * radius, sy * radius, z) + N);
+}
+__device__ __forceinline__ float cosine_weighted_pdf(f3 N, f3 omega) { return omax(dot3(N, omega) / PI_F, 0.0f); } // shading.odin:37-39
+// surface_sampling (shading.odin:41-50): uniform light triangle, uniform point on it
+__device__ __forceinline__ f3 surface_sampling(const SceneDev& s, f3 P, uint32_t r1, uint32_t r2, uint32_t r3) {
+    const uint32_t idx = (uint32_t)(((uint64_t)r1 * (uint64_t)(uint32_t)s.n_lights) >> 32);
+    const float4* lp = s.ltris + (size_t)idx * 4;
+    const float4 la = ldg4(lp), lb = ldg4(lp + 1), lc = ldg4(lp + 2);
+    float su = u01(r2) * (1.0f - 0.0f) + 0.0f, sv = u01(r3) * (1.0f - 0.0f) + 0.0f;
+    if (su + sv > 1.0f) { su = 1.0f - su; sv = 1.0f - sv; }
+    const f3 world = mk3(la.x, la.y, la.z) + su * mk3(la.w, lb.x, lb.y) + sv * mk3(lb.z, lb.w, lc.x);
+    return normalize3(world - P);
+}
+// sample (shading.odin:139-151): r0 picks the strategy, r1.. are the strategy's draws in source order
+__device__ __forceinline__ f3 sample_dir(const SceneDev& s, f3 N, f3 P, float roughness, f3 in_d, const Philox4& rr) {
+    const float tsel = u01(rr.r0);
+    if (tsel <= 0.33333f) return cosine_weighted(N, rr.r1, rr.r2);
+    if (tsel < 0.666666f && s.n_lights > 0) return surface_sampling(s, P, rr.r1, rr.r2, rr.r3);
+    const f3 hn = vndf_sampling(N, -in_d, sq(roughness), u01(rr.r1), u01(rr.r2));
+    return in_d - 2.0f * dot3(hn, in_d) * hn;
+}
+// pdf (shading.odin:153-162) from its three terms: the light term is the light-BVH all-hit sum of the
+// ray (k_trace<true>) / len(light_surfaces); vndf_term already carries the (1 if has_lights else 2)
+__device__ __forceinline__ float vndf_pdf_term(const SceneDev& s, f3 N, f3 in_d, float roughness, f3 nd) {
+    return vndf_sampling_pdf(N, -in_d, sq(roughness), nd) * (s.n_lights > 0 ? 1.0f : 2.0f);
+}
+__device__ __forceinline__ float complete_pdf(const SceneDev& s, float cos_pdf, float lsum, float vndf_term) {
+    const float lp = s.n_lights > 0 ? lsum / (float)s.n_lights : 0.0f;
+    return (cos_pdf + lp + vndf_term) / 3.0f;
+}
+// miss: equirectangular environment lookup (raytracer.odin:437-446)
+__device__ __forceinline__ float4 env_lookup(const SceneDev& s, float dx, float dy, float dz) {
+    const float tu = 0.5f + atan2f(dz, dx) / TAU_F;
+    const float tv = 0.5f - asinf(dy) / PI_F;
+    return texture_sample(s.env, false, tu, tv);
+}
+
 // ------------------------------------------------------------------------------------------------
 // k_shade: one wavefront step of raytrace (raytracer.odin:432-500) in iterative form.
 // Path state: L = sum_k T_k * emission_k lives in st_c BY SLOT and is only touched when a hit adds
@@ -430,8 +462,7 @@ k_shade(const SceneDev s, const RenderParams p, const ShadeArgs a) {
                 const float4 pa = a.pa_in[pos], pb = a.pb_in[pos];
                 const f3 value = mk3(pb.x, pb.y, pb.z);
                 // pdf (shading.odin:158-161): (cosine + light + vndf * (1 | 2)) / 3
-                const float lp = has_lights ? a.lsum[pos] / (float)s.n_lights : 0.0f;
-                const float pdf = (pa.w + lp + pb.w) / 3.0f;
+                const float pdf = complete_pdf(s, pa.w, has_lights ? a.lsum[pos] : 0.0f, pb.w);
                 if (norm_l1(value) / pdf > 1e-5f) T = mk3(pa.x, pa.y, pa.z) * value / pdf;
                 else alive = false; // exitance = emission only: L already holds it
             }
@@ -442,9 +473,7 @@ k_shade(const SceneDev s, const RenderParams p, const ShadeArgs a) {
                     if (s.has_env) {
                         const float4 d4 = a.qd_in[pos];
                         const uint32_t slot = __float_as_uint(a.qo_in[pos].w);
-                        const float tu = 0.5f + atan2f(d4.z, d4.x) / TAU_F;
-                        const float tv = 0.5f - asinf(d4.y) / PI_F;
-                        const float4 e = texture_sample(s.env, false, tu, tv);
+                        const float4 e = env_lookup(s, d4.x, d4.y, d4.z);
                         const float4 c = a.st_c[slot];
                         const f3 L = mk3(c.x, c.y, c.z) + T * mk3(e.x, e.y, e.z);
                         a.st_c[slot] = make_float4(L.x, L.y, L.z, 0.0f);
@@ -567,33 +596,14 @@ k_shade(const SceneDev s, const RenderParams p, const ShadeArgs a) {
                 const uint64_t smp = p.sample_base + s_local;
                 const Philox4 rr = philox4x32_10(pix, (uint32_t)smp, (uint32_t)(smp >> 32), 1u + (uint32_t)bounce,
                                                  (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
-                const float tsel = u01(rr.r0);
-                if (tsel <= 0.33333f) {
-                    const float phi = u01(rr.r1) * (TAU_F - 0.0f) + 0.0f; // sphere_uniform shading.odin:9-15
-                    const float z = u01(rr.r2) * (1.0f - -1.0f) + -1.0f;
-                    float sx, sy;
-                    sincosf(phi, &sx, &sy);
-                    const float radius = sqrtf(1.0f - sq(z));
-                    nd = normalize3(mk3(sx * radius, sy * radius, z) + N);
-                } else if (tsel < 0.666666f && has_lights) {
-                    const uint32_t idx = (uint32_t)(((uint64_t)rr.r1 * (uint64_t)(uint32_t)s.n_lights) >> 32);
-                    const float4* lp = s.ltris + (size_t)idx * 4;
-                    const float4 la = ldg4(lp), lb = ldg4(lp + 1), lc = ldg4(lp + 2);
-                    float su = u01(rr.r2) * (1.0f - 0.0f) + 0.0f, sv = u01(rr.r3) * (1.0f - 0.0f) + 0.0f;
-                    if (su + sv > 1.0f) { su = 1.0f - su; sv = 1.0f - sv; }
-                    const f3 world = mk3(la.x, la.y, la.z) + su * mk3(la.w, lb.x, lb.y) + sv * mk3(lb.z, lb.w, lc.x);
-                    nd = normalize3(world - P);
-                } else {
-                    const f3 hn = vndf_sampling(N, -in_d, sq(roughness), u01(rr.r1), u01(rr.r2));
-                    nd = in_d - 2.0f * dot3(hn, in_d) * hn;
-                }
+                nd = sample_dir(s, N, P, roughness, in_d, rr);
                 value = brdf_cos(color, N, metallic, roughness, in_d, nd);
                 // norm_l1(value)/pdf > 1e-5 can only hold for norm_l1(value) > 0
                 if (!(norm_l1(value) > 0.0f)) cont = false;
             }
             if (cont) {
-                const float cos_pdf = omax(dot3(N, nd) / PI_F, 0.0f); // shading.odin:37-39
-                const float vndf_term = vndf_sampling_pdf(N, -in_d, sq(roughness), nd) * (has_lights ? 1.0f : 2.0f);
+                const float cos_pdf = cosine_weighted_pdf(N, nd);
+                const float vndf_term = vndf_pdf_term(s, N, in_d, roughness, nd);
                 emit = true;
                 out_a = make_float4(T.x, T.y, T.z, cos_pdf);
                 out_b = make_float4(value.x, value.y, value.z, vndf_term);
@@ -674,8 +684,16 @@ k_shade(const SceneDev s, const RenderParams p, const ShadeArgs a) {
 
 // ------------------------------------------------------------------------------------------------
 // k_resolve: rc_set_pixel (main.odin:89-102) for every sample of the wave, in sample order.
-// accum planes: total.rgb | total_squared.rgb | count | reserved, index (H-1-y)*W + x.
+// accum planes: total.rgb | total_squared.rgb | count_lo | count_hi, index (H-1-y)*W + x.
+// Sample_Stats.count is a u32 (main.odin:36): the count is kept as count_lo + 2^20 * count_hi with
+// count_lo < 2^20 after every wave, so both planes stay exact integers in f32 — also under the one
+// float sum-reduce over up to 16 GPUs — however many waves a caller accumulates.
 // ------------------------------------------------------------------------------------------------
+constexpr float COUNT_RADIX = 1048576.0f; // 2^20
+__device__ __forceinline__ uint32_t accum_count(const float* accum, uint32_t npix, uint32_t i) {
+    const unsigned long long c = (unsigned long long)accum[6 * npix + i] + ((unsigned long long)accum[7 * npix + i] << 20);
+    return c > 0xffffffffull ? 0xffffffffu : (uint32_t)c;
+}
 __global__ void k_resolve(const RenderParams p, const float4* __restrict__ st_c, float* __restrict__ accum,
                           float* __restrict__ first, float* __restrict__ last, const int write_first,
                           const int write_last) {
@@ -694,7 +712,9 @@ __global__ void k_resolve(const RenderParams p, const float4* __restrict__ st_c,
         }
         accum[i] = tr; accum[npix + i] = tg; accum[2 * npix + i] = tb;
         accum[3 * npix + i] = qr; accum[4 * npix + i] = qg; accum[5 * npix + i] = qb;
-        accum[6 * npix + i] += (float)p.n_batch_samples;
+        float lo = accum[6 * npix + i] + (float)p.n_batch_samples, hi = accum[7 * npix + i];
+        while (lo >= COUNT_RADIX) { lo -= COUNT_RADIX; hi += 1.0f; }
+        accum[6 * npix + i] = lo; accum[7 * npix + i] = hi;
         if (write_last) { last[i] = c.x; last[npix + i] = c.y; last[2 * npix + i] = c.z; }
     }
 }
@@ -719,6 +739,66 @@ __global__ void k_stats(const uint32_t* __restrict__ counts, const uint32_t* __r
 }
 
 // ---- probes / packing ---------------------------------------------------------------------------
+// ort_probe_shading: one evaluation per thread of the device functions k_shade calls (record layouts in
+// include/odinrt_b200.h).  `lsum` = light-BVH sums of the ORT_PROBE_PDF rays (k_trace<true> ran first).
+__host__ __device__ inline int probe_in_floats(int kind) {
+    return kind == 0 ? 14 : kind == 1 ? 9 : kind == 2 ? 10 : kind == 3 ? 14 : kind == 4 ? 13 : kind == 5 ? 4 : kind == 6 ? 5 : 3;
+}
+__host__ __device__ inline int probe_out_floats(int kind) {
+    return kind == 2 || kind == 4 ? 1 : kind == 5 || kind == 6 ? 4 : 3;
+}
+__global__ void k_probe_pack(const float* __restrict__ in, const uint32_t n, float4* __restrict__ qo, float4* __restrict__ qd,
+                             uint32_t* __restrict__ count0) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *count0 = n;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float* x = in + (size_t)i * 13; // ORT_PROBE_PDF: n[3] pos[3] roughness in_d[3] out_d[3]
+        qo[i] = make_float4(x[3], x[4], x[5], __uint_as_float(i));
+        qd[i] = make_float4(x[10], x[11], x[12], 0.0f);
+    }
+}
+__global__ void k_probe(const SceneDev s, const int kind, const float* __restrict__ in, const uint32_t n,
+                        float* __restrict__ out, const float* __restrict__ lsum) {
+    const int ni = probe_in_floats(kind), no = probe_out_floats(kind);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float* x = in + (size_t)i * ni;
+        float* o = out + (size_t)i * no;
+        switch (kind) {
+        case 0: {
+            const f3 v = brdf_cos(mk3(x[3], x[4], x[5]), mk3(x[0], x[1], x[2]), x[6], x[7], mk3(x[8], x[9], x[10]), mk3(x[11], x[12], x[13]));
+            o[0] = v.x; o[1] = v.y; o[2] = v.z;
+        } break;
+        case 1: {
+            const f3 v = vndf_sampling(mk3(x[0], x[1], x[2]), mk3(x[3], x[4], x[5]), x[6], x[7], x[8]);
+            o[0] = v.x; o[1] = v.y; o[2] = v.z;
+        } break;
+        case 2: o[0] = vndf_sampling_pdf(mk3(x[0], x[1], x[2]), mk3(x[3], x[4], x[5]), x[6], mk3(x[7], x[8], x[9])); break;
+        case 3: {
+            Philox4 rr;
+            rr.r0 = __float_as_uint(x[10]); rr.r1 = __float_as_uint(x[11]); rr.r2 = __float_as_uint(x[12]); rr.r3 = __float_as_uint(x[13]);
+            const f3 v = sample_dir(s, mk3(x[0], x[1], x[2]), mk3(x[3], x[4], x[5]), x[6], mk3(x[7], x[8], x[9]), rr);
+            o[0] = v.x; o[1] = v.y; o[2] = v.z;
+        } break;
+        case 4: {
+            const f3 N = mk3(x[0], x[1], x[2]), in_d = mk3(x[7], x[8], x[9]), nd = mk3(x[10], x[11], x[12]);
+            o[0] = complete_pdf(s, cosine_weighted_pdf(N, nd), s.n_lights > 0 ? lsum[i] : 0.0f, vndf_pdf_term(s, N, in_d, x[6], nd));
+        } break;
+        case 5: {
+            const int ti = __float_as_int(x[0]);
+            const float4 v = texture_sample(ti < 0 ? s.env : s.texs[ti], x[1] != 0.0f, x[2], x[3]);
+            o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+        } break;
+        case 6: {
+            const f3 N = mk3(x[0], x[1], x[2]);
+            const f3 v = cosine_weighted(N, __float_as_uint(x[3]), __float_as_uint(x[4]));
+            o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = cosine_weighted_pdf(N, v);
+        } break;
+        default: {
+            const float4 v = env_lookup(s, x[0], x[1], x[2]);
+            o[0] = v.x; o[1] = v.y; o[2] = v.z;
+        } break;
+        }
+    }
+}
 __global__ void k_pack_rays(const float* __restrict__ rays6, const uint32_t n, float4* __restrict__ qo,
                             float4* __restrict__ qd, uint32_t* __restrict__ count0) {
     if (blockIdx.x == 0 && threadIdx.x == 0) *count0 = n;
@@ -785,19 +865,37 @@ __global__ void k_pack_stats(const float* __restrict__ accum, const float* __res
             o[7 + c] = __float_as_uint(accum[c * npix + i]);
             o[10 + c] = __float_as_uint(accum[(3 + c) * npix + i]);
         }
-        o[3] = (uint32_t)accum[6 * npix + i];
+        o[3] = accum_count(accum, npix, i);
     }
 }
 
-// get_rgb_image, mode Mean (output.odin:21-80)
+// Sample_Stats AoS -> planar accumulators + first / last planes (ort_frame_load: a resumed checkpoint)
+__global__ void k_unpack_stats(const uint32_t* __restrict__ in13, const uint32_t npix, float* __restrict__ accum,
+                               float* __restrict__ first, float* __restrict__ last) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
+        const uint32_t* o = in13 + (size_t)i * 13;
+        for (int c = 0; c < 3; c++) {
+            first[c * npix + i] = __uint_as_float(o[c]);
+            last[c * npix + i] = __uint_as_float(o[4 + c]);
+            accum[c * npix + i] = __uint_as_float(o[7 + c]);
+            accum[(3 + c) * npix + i] = __uint_as_float(o[10 + c]);
+        }
+        accum[6 * npix + i] = (float)(o[3] & 0xfffffu);
+        accum[7 * npix + i] = (float)(o[3] >> 20);
+    }
+}
+
+// get_rgb_image, mode Mean (output.odin:21-80).  The gamma power is evaluated in f64 and rounded once to f32:
+// that is the correctly rounded powf(tm, 1/2.2f) (bar double-rounding cases rarer than 1 in 2^27), which is what
+// the oracle's glibc powf returns — CUDA's f32 powf (up to 2 ulp off) would flip a byte at rounding boundaries.
 __global__ void k_tonemap(const float* __restrict__ accum, const uint32_t npix, uint8_t* __restrict__ rgb) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
-        const float cnt = accum[6 * npix + i];
+        const float cnt = (float)accum_count(accum, npix, i);
         for (int c = 0; c < 3; c++) {
             float x = omax(accum[c * npix + i] / cnt, 0.0f);
             float tm = (x * (2.51f * x + 0.03f)) / (x * (2.43f * x + 0.59f) + 0.14f);
             tm = fminf(fmaxf(tm, 0.0f), 1.0f);
-            const float g = powf(tm, (float)(1.0 / 2.2));
+            const float g = (float)pow((double)tm, (double)(float)(1.0 / 2.2));
             rgb[3 * (size_t)i + c] = (uint8_t)roundf(g * 255.0f);
         }
     }

@@ -8,6 +8,8 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -42,7 +44,7 @@ struct ort_ctx {
     // re-uploading a scene of the same shape performs no cudaMalloc / cudaFree (a cudaFree was
     // measured at 15-600 ms on B200 boxes: it synchronises the device and unmaps).
     struct DevBuf { void* p = nullptr; size_t cap = 0, used = 0; };
-    enum { SB_NODES, SB_TRIS, SB_LLIGHT, SB_MATS, SB_TSHADE, SB_TUV, SB_TTAN, SB_TEXS, SB_NODES8, SB_TRIS8, SB_NODES8X, SB_COUNT };
+    enum { SB_NODES, SB_TRIS, SB_LLIGHT, SB_MATS, SB_TSHADE, SB_TUV, SB_TTAN, SB_TEXS, SB_COUNT };
     DevBuf sbuf[SB_COUNT];
     struct TexSlot { cudaArray_t arr = nullptr; cudaTextureObject_t obj = 0; size_t w = 0, h = 0; bool in_use = false; };
     std::vector<TexSlot> tex_pool;
@@ -54,14 +56,8 @@ struct ort_ctx {
     int stage_next = 0;
     int host_threads = 1;
     int64_t n_tris = 0, n_ltris = 0;
-    WideBVH wide, lwide;
-    Wide8BVH wide8, lwide8;
-    Wide8xBVH wide8x, lwide8x;
-    bool use8x = false; // ORT_BVH8=2: exact-order 8-wide traversal (k_trace<.., .., 2>)
-    int trace8x_grid[2] = {0, 0};
-    int bvh8 = 0;      // env ORT_BVH8=1: traverse the 8-wide re-emission (k_trace8)
-    bool use8 = false; // the uploaded scene has an 8-wide tree
-    int trace8_grid[2] = {0, 0};
+    int64_t wide_nodes = 0, wide_depth = 0, wide_max_stack = 0, lwide_nodes = 0;
+    int64_t ref_stack_need = 0; // worst-case occupancy of the REFERENCE's 64-entry stack on this scene's binary BVH
     int64_t scene_bytes = 0;
 
     // path buffers: two independent wave pipelines (ps[1] only when waves are overlapped)
@@ -76,12 +72,31 @@ struct ort_ctx {
         int64_t capacity = 0;
         int counters_depth = 0;
         cudaEvent_t resolved = nullptr; // recorded after this pipeline's k_resolve + k_stats
+        bool used = false;              // `resolved` has been recorded at least once
     } ps[MAX_PIPES];
     cudaStream_t aux_stream[MAX_PIPES] = {}; // pipelines 1.. (0 runs on `stream`)
     cudaEvent_t ev_fork = nullptr, ev_join[MAX_PIPES] = {};
-    int overlap = 4;                    // number of overlapped wave pipelines (env ORT_OVERLAP=1..4)
+    int overlap = 4;                    // number of overlapped wave pipelines (env ORT_OVERLAP=1..8)
     unsigned long long* d_stats = nullptr;
     int64_t path_bytes = 0;
+    int64_t max_path_bytes = 0;         // ort_device_cfg.max_path_bytes: pretend only this much HBM is free for path state
+    uint64_t last_done = 0;             // samples per pixel the last render call completed
+    uint64_t wave_seq = 0;              // waves enqueued so far (picks the pipeline; persistent across ort_frame_render calls)
+    cudaEvent_t last_resolved = nullptr; // `resolved` of the most recently enqueued wave: the next accumulation waits for it
+    bool pipes_busy = false;            // chained waves may still be running on aux streams that ctx->stream has not joined
+    bool need_fork = true;              // ctx->stream holds work the other pipelines must wait for before their next wave
+    int chain_pipes = 0;
+
+    // device-resident frame (ort_frame_*): 8 accumulator planes + 3 first + 3 last, w*h floats each
+    float* frame = nullptr;
+    size_t frame_bytes = 0;
+    uint32_t frame_w = 0, frame_h = 0;
+    bool frame_has_first = false;       // the `first` planes are already written (first wave done, or loaded)
+    bool frame_snapshot_valid = false;  // ort_frame_snapshot was taken and not consumed yet
+    cudaStream_t side_stream = nullptr; // preview / fetch of the snapshot run here, next to the render pipelines
+    cudaEvent_t snap_ev = nullptr;
+    void* side_buf = nullptr;           // packed Sample_Stats / RGB8 staging of the side stream
+    size_t side_bytes = 0;
 
     // scratch for host-facing calls
     float* scratch = nullptr;
@@ -89,16 +104,16 @@ struct ort_ctx {
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
 
-    int trace_grid[2][3] = {{0, 0, 0}, {0, 0, 0}}; // [node encoding][mode] persistent grid sizes
+    int trace_grid[2] = {0, 0}; // persistent grid sizes: closest hit, light sum
     int shade_grid = 0;
-    bool quant = false; // scene uses QuantNode
-    int tiled = 2;    // env ORT_TILED: 0 = primary rays in pixel order, 1 = 8x4 pixel tiles, 2 = 2x2 pixels x 8 samples per warp (ORT_TILE=WxHxS)
-    int exp_ctas = 0; // env ORT_EXP_CTAS=n: occupancy experiment, at most n traversal CTAs per SM
-    int fuse = 0; // env ORT_FUSE=1: trace closest hit + light sum in one fused pass
-    int bin_octants = 1;     // env ORT_BIN=0: plain per-warp queue compaction (no direction-octant binning)
-    int light_prefilter = 1; // env ORT_LIGHT_PREFILTER=0: send every continuation ray through the light pass
-    int refill = ORT_REFILL_THRESHOLD; // dynamic-fetch threshold (env ORT_REFILL, for tuning)
-    int inner_min = ORT_INNER_MIN;     // inner-loop early-exit threshold (env ORT_INNER_MIN, for tuning)
+    // tuning knobs: fixed at their measured optimum in the shipped library; a -DORT_TUNING build
+    // (make variant) reads them from the environment for tools/tune.py
+    int tiled = 2;           // 0 = primary rays in pixel order, 1 = 8x4 pixel tiles, 2 = tile_w x tile_h pixels x tile_s samples per warp
+    int tile_w = 2, tile_h = 2, tile_s = 8;
+    int bin_octants = 1;     // 0: plain per-warp queue compaction (no direction-octant binning)
+    int light_prefilter = 1; // 0: send every continuation ray through the light pass
+    int refill = ORT_REFILL_THRESHOLD; // dynamic-fetch threshold
+    int inner_min = ORT_INNER_MIN;     // inner-loop early-exit threshold
     bool profiling = false;
     double ms_trace = 0, ms_light = 0, ms_shade = 0, ms_other = 0, ms_render = 0;
     uint64_t launches = 0;
@@ -117,6 +132,44 @@ int fail(ort_ctx* c, const std::string& msg) {
         if (e_ != cudaSuccess)                                                                     \
             return fail(ctx, std::string(#call) + ": " + cudaGetErrorString(e_));                  \
     } while (0)
+
+// No C++ exception crosses the C ABI (std::thread, std::vector can throw): report it like any other error.
+template <typename F>
+int guarded(ort_ctx* ctx, F f) {
+    try {
+        return f();
+    } catch (const std::exception& e) {
+        return fail(ctx, std::string("exception: ") + e.what());
+    } catch (...) {
+        return fail(ctx, "unknown C++ exception");
+    }
+}
+
+// The 4-wide re-emission of the scene and light BVHs (+ the reference's own worst-case stack need), built
+// once per upload — and once for ALL devices of an ort_multi.
+struct SharedWide {
+    WideBVH wide, lwide;
+    bool ok_scene = false, ok_light = false;
+    const char* why_scene = "not built";
+    const char* why_light = "not built";
+    int64_t ref_stack_need = 0;
+    std::mutex mu;
+    std::condition_variable cv;
+    bool ready = false;
+    void build(const ort_scene* sc) {
+        try {
+            ok_scene = build_wide_bvh(sc->bvh, sc->n_bvh_nodes, sc->n_triangles, &wide, &why_scene);
+            ok_light = build_wide_bvh(sc->light_bvh, sc->n_light_bvh_nodes, sc->n_light_triangles, &lwide, &why_light);
+            if (ok_scene) ref_stack_need = reference_stack_need(sc->bvh, sc->n_bvh_nodes);
+        } catch (...) {
+            ok_scene = false; why_scene = "out of host memory";
+        }
+        { std::lock_guard<std::mutex> l(mu); ready = true; }
+        cv.notify_all();
+    }
+    void wait() { std::unique_lock<std::mutex> l(mu); cv.wait(l, [&] { return ready; }); }
+};
+int upload_scene_impl(ort_ctx* ctx, const ort_scene* sc, SharedWide* shared);
 
 // ORT_TIMING=1: wall-clock phases of the host-facing calls on stderr (diagnostic)
 struct PhaseTimer {
@@ -323,8 +376,8 @@ int make_texture(ort_ctx* ctx, const ort_texture& t, bool srgb, cudaTextureObjec
 }
 
 int ensure_paths(ort_ctx* ctx, int64_t need, int pipes = 1) {
-    if (const char* lim = std::getenv("ORT_TEST_MAX_PATH_BYTES")) // test hook: pretend the GPU has only this much room
-        if ((double)need * (16 * 10 + 12) * pipes > std::atof(lim)) return fail(ctx, "cudaMalloc: out of memory (simulated)");
+    if (ctx->max_path_bytes > 0 && (double)need * (16 * 10 + 12) * pipes > (double)ctx->max_path_bytes)
+        return fail(ctx, "cudaMalloc: out of memory (ort_device_cfg.max_path_bytes)");
     for (int i = 0; i < pipes; i++) {
         auto& P = ctx->ps[i];
         if (P.capacity >= need) continue;
@@ -378,7 +431,7 @@ int ensure_pinned(ort_ctx* ctx, size_t bytes) {
     return 0;
 }
 
-// mode 0: closest hit, 1: light-pdf sum, 2: both fused in one pass
+// mode 0: closest hit, 1: light-pdf sum
 void launch_trace(ort_ctx* ctx, ort_ctx::PathSet& P, cudaStream_t st, const float4* qo, const float4* qd,
                   const uint32_t* n_ptr, uint32_t* work_ctr, int mode, float* lsum = nullptr,
                   const uint32_t* index = nullptr) {
@@ -386,31 +439,8 @@ void launch_trace(ort_ctx* ctx, ort_ctx::PathSet& P, cudaStream_t st, const floa
     a.qo = qo; a.qd = qd; a.n_ptr = n_ptr; a.work_ctr = work_ctr; a.index = index;
     a.hits = P.hits; a.lsum = lsum ? lsum : P.lsum;
     a.refill_threshold = ctx->refill; a.inner_min = ctx->inner_min;
-    if (ctx->use8x && mode < 2) {
-        if (mode == 0) k_trace<true, false, 2><<<ctx->trace8x_grid[0], TRACE_THREADS, 0, st>>>(ctx->sd, a);
-        else k_trace<false, true, 2><<<ctx->trace8x_grid[1], TRACE_THREADS, 0, st>>>(ctx->sd, a);
-        ctx->launches++;
-        return;
-    }
-    if (ctx->use8 && mode < 2) {
-        if (mode == 0) k_trace8<true><<<ctx->trace8_grid[0], TRACE_THREADS, 0, st>>>(ctx->sd, a);
-        else k_trace8<false><<<ctx->trace8_grid[1], TRACE_THREADS, 0, st>>>(ctx->sd, a);
-        ctx->launches++;
-        return;
-    }
-    int g = ctx->trace_grid[ctx->quant ? 1 : 0][mode];
-    // sensitivity experiment (ORT_EXP_CTAS=n): cap the resident CTAs per SM with unused dynamic shared memory
-    const size_t dsm = ctx->exp_ctas > 0 ? (size_t)(200 * 1024 / ctx->exp_ctas - 17 * 1024) : 0;
-    if (ctx->exp_ctas > 0) g = std::min(g, ctx->sm_count * ctx->exp_ctas);
-    if (!ctx->quant) {
-        if (mode == 0) k_trace<true, false, false><<<g, TRACE_THREADS, dsm, st>>>(ctx->sd, a);
-        else if (mode == 1) k_trace<false, true, false><<<g, TRACE_THREADS, dsm, st>>>(ctx->sd, a);
-        else k_trace<true, true, false><<<g, TRACE_THREADS, 0, st>>>(ctx->sd, a);
-    } else {
-        if (mode == 0) k_trace<true, false, true><<<g, TRACE_THREADS, 0, st>>>(ctx->sd, a);
-        else if (mode == 1) k_trace<false, true, true><<<g, TRACE_THREADS, 0, st>>>(ctx->sd, a);
-        else k_trace<true, true, true><<<g, TRACE_THREADS, 0, st>>>(ctx->sd, a);
-    }
+    if (mode == 0) k_trace<false><<<ctx->trace_grid[0], TRACE_THREADS, 0, st>>>(ctx->sd, a);
+    else k_trace<true><<<ctx->trace_grid[1], TRACE_THREADS, 0, st>>>(ctx->sd, a);
     ctx->launches++;
 }
 
@@ -454,7 +484,7 @@ int launch_wave(ort_ctx* ctx, ort_ctx::PathSet& P, cudaStream_t st, cudaEvent_t 
     uint32_t* used = P.counters + 3 * (D + 2);
     uint32_t* lcount = P.counters + 4 * (D + 2);
     const bool lights = ctx->sd.n_lights > 0;
-    const int prefilter = (ctx->light_prefilter && !ctx->quant) ? 1 : 0;
+    const int prefilter = ctx->light_prefilter ? 1 : 0;
     {
         Prof pr(ctx, &ctx->ms_other);
         CK(cudaMemsetAsync(P.counters, 0, sizeof(uint32_t) * 5 * (size_t)(D + 2), st));
@@ -470,9 +500,9 @@ int launch_wave(ort_ctx* ctx, ort_ctx::PathSet& P, cudaStream_t st, cudaEvent_t 
         float* lsum_out = P.lsum + (size_t)out * (size_t)P.capacity;
         {
             Prof pr(ctx, &ctx->ms_trace);
-            launch_trace(ctx, P, st, P.qo[in], P.qd[in], counts + k, wtrace + k, (need_light && ctx->fuse) ? 2 : 0, lsum_in);
+            launch_trace(ctx, P, st, P.qo[in], P.qd[in], counts + k, wtrace + k, 0, lsum_in);
         }
-        if (need_light && !ctx->fuse) {
+        if (need_light) {
             // only the rays k_shade queued as light candidates (the others already have lsum = 0)
             Prof pr(ctx, &ctx->ms_light);
             launch_trace(ctx, P, st, P.qo[in], P.qd[in], lcount + k, wlight + k, 1, lsum_in, P.lq);
@@ -485,7 +515,7 @@ int launch_wave(ort_ctx* ctx, ort_ctx::PathSet& P, cudaStream_t st, cudaEvent_t 
             sa.qo_out = P.qo[out]; sa.qd_out = P.qd[out]; sa.pa_out = P.pa[out]; sa.pb_out = P.pb[out];
             sa.n_out_ptr = counts + k + 1; sa.used_ptr = used + k; sa.st_c = P.st_c;
             sa.lsum_out = lsum_out; sa.lq = P.lq; sa.lq_count = lcount + k + 1;
-            sa.bounce = k; sa.prefilter = ctx->fuse ? 0 : prefilter; sa.bin_octants = ctx->bin_octants;
+            sa.bounce = k; sa.prefilter = prefilter; sa.bin_octants = ctx->bin_octants;
             k_shade<<<ctx->shade_grid, 256, 0, st>>>(ctx->sd, p, sa);
             ctx->launches++;
         }
@@ -494,7 +524,7 @@ int launch_wave(ort_ctx* ctx, ort_ctx::PathSet& P, cudaStream_t st, cudaEvent_t 
         Prof pr(ctx, &ctx->ms_other);
         if (wait_for) CK(cudaStreamWaitEvent(st, wait_for, 0));
         k_resolve<<<ctx->shade_grid, 256, 0, st>>>(p, P.st_c, d_accum, d_first, d_last, write_first, write_last);
-        k_stats<<<1, 32, 0, st>>>(counts, used, ctx->fuse ? counts : lcount, D, lights ? 1 : 0, ctx->d_stats);
+        k_stats<<<1, 32, 0, st>>>(counts, used, lcount, D, lights ? 1 : 0, ctx->d_stats);
         ctx->launches += 2;
         CK(cudaEventRecord(P.resolved, st));
     }
@@ -502,8 +532,27 @@ int launch_wave(ort_ctx* ctx, ort_ctx::PathSet& P, cudaStream_t st, cudaEvent_t 
     return 0;
 }
 
+// Make ctx->stream wait for everything enqueued on the other pipelines' streams.
+int join_pipes(ort_ctx* ctx) {
+    if (!ctx->pipes_busy) return 0;
+    for (int i = 1; i < MAX_PIPES; i++) {
+        CK(cudaEventRecord(ctx->ev_join[i], ctx->aux_stream[i]));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[i], 0));
+    }
+    ctx->pipes_busy = false;
+    ctx->last_resolved = nullptr; // later waves are ordered behind ctx->stream by the next fork
+    ctx->need_fork = true;
+    return 0;
+}
+
+// chain = false (ort_render, ort_render_device): fork the pipelines off ctx->stream, enqueue the waves, join
+// them back — everything of this call is complete once ctx->stream reaches the end of the call.
+// chain = true (ort_frame_render): the pipelines keep running ACROSS calls — wave k of the frame runs on
+// pipeline k % pipes whichever call enqueued it, its accumulation waits for wave k-1's, and nothing joins
+// at the end of the call, so consecutive calls leave no drain / ramp-up gap on the device.
 int render_impl(ort_ctx* ctx, uint32_t w, uint32_t h, int32_t depth, uint64_t first_sample, uint64_t n_samples,
-                float* d_accum, float* d_first, float* d_last, const volatile uint8_t* interrupt, uint64_t* done_out) {
+                float* d_accum, float* d_first, float* d_last, const volatile uint8_t* interrupt, uint64_t* done_out,
+                bool chain = false) {
     if (!ctx->has_scene) return fail(ctx, "ort_upload_scene has not been called");
     if (w == 0 || h == 0) return fail(ctx, "width and height must be non-zero");
     if (depth < 0) return fail(ctx, "ray_depth must be >= 0");
@@ -512,66 +561,83 @@ int render_impl(ort_ctx* ctx, uint32_t w, uint32_t h, int32_t depth, uint64_t fi
     int64_t cap = ctx->capacity_cfg > 0 ? ctx->capacity_cfg : ((int64_t)1 << 25); // paths per wave (x up to 4 overlapped waves)
     if ((uint64_t)cap < npix) cap = (int64_t)npix;
     uint64_t per_wave = std::max<uint64_t>(1, (uint64_t)cap / npix);
-    if (per_wave > n_samples) per_wave = std::max<uint64_t>(n_samples, 1);
+    if (!chain && per_wave > n_samples) per_wave = std::max<uint64_t>(n_samples, 1);
     // several wave pipelines on separate streams: the tail of every persistent kernel of one wave (a
     // few warps finishing their last rays) is filled by the other waves' kernels
-    int pipes = 1;
+    int pipes = 1, overlap = ctx->overlap; // a fallback below de-tunes THIS call only
+    ctx->last_done = 0;
+    if (done_out) *done_out = 0;
+    if (!chain && join_pipes(ctx)) return 1; // waves of an earlier ort_frame_render may still be in flight
     for (;;) {
         const uint64_t n_waves = (n_samples + per_wave - 1) / per_wave;
-        pipes = std::max(1, std::min(ctx->overlap, MAX_PIPES));
+        pipes = std::max(1, std::min(overlap, MAX_PIPES));
         if (ctx->profiling || depth == 0) pipes = 1;
-        if ((uint64_t)pipes > n_waves) pipes = (int)n_waves;
+        if (!chain && (uint64_t)pipes > n_waves) pipes = (int)n_waves;
+        if (pipes < 1) pipes = 1;
+        if (ctx->pipes_busy && (pipes != ctx->chain_pipes || (int64_t)(per_wave * npix) > ctx->ps[0].capacity) && join_pipes(ctx)) return 1;
         if (ensure_paths(ctx, (int64_t)(per_wave * npix), pipes) == 0) break;
         // not enough free HBM for this many paths in flight (other contexts / processes on the GPU):
         // fall back to smaller waves, then to fewer pipelines, before giving up
         cudaGetLastError();
+        if (join_pipes(ctx)) return 1;
+        CK(cudaStreamSynchronize(ctx->stream));
         free_paths(ctx);
         if (per_wave > 1) per_wave = (per_wave + 1) / 2;
-        else if (ctx->overlap > 1) ctx->overlap = 1;
+        else if (overlap > 1) overlap = 1;
         else return 1; // ctx->err holds the cudaMalloc message
     }
     if (ensure_counters(ctx, depth, pipes)) return 1;
     RenderParams p;
     fill_params(ctx, w, h, depth, &p);
     p.tiled = ctx->tiled;
-    if (const char* e2 = std::getenv("ORT_TILE")) { int a_ = 2, b_ = 2, c_ = 8; if (std::sscanf(e2, "%dx%dx%d", &a_, &b_, &c_) == 3 && a_ * b_ * c_ == 32) { p.tile_w = a_; p.tile_h = b_; p.tile_s = c_; } }
-    CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    if (pipes > 1) {
+    p.tile_w = ctx->tile_w; p.tile_h = ctx->tile_h; p.tile_s = ctx->tile_s;
+    if (!chain) CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (pipes > 1 && (!chain || ctx->need_fork)) {
+        // the other pipelines start behind whatever ctx->stream already holds (scene upload, cleared accumulators)
         CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
         for (int i = 1; i < pipes; i++) CK(cudaStreamWaitEvent(ctx->aux_stream[i], ctx->ev_fork, 0));
     }
-    uint64_t done = 0, wave = 0;
-    cudaEvent_t prev = nullptr;
+    ctx->need_fork = false;
+    if (!chain) { ctx->wave_seq = 0; ctx->last_resolved = nullptr; }
+    uint64_t done = 0;
     while (done < n_samples) {
         if (interrupt && *interrupt) break; // is_interrupted(), raytracer.odin:554
         const uint64_t nb = std::min<uint64_t>(per_wave, n_samples - done);
         p.sample_base = first_sample + done;
         p.n_batch_samples = (uint32_t)nb;
-        const int pi = (int)(wave % (uint64_t)pipes);
+        const int pi = (int)(ctx->wave_seq % (uint64_t)pipes);
         cudaStream_t st = pi ? ctx->aux_stream[pi] : ctx->stream;
         // with an interrupt flag the host stays at most `pipes` waves ahead of the device (it waits for
         // the wave that last used this pipeline), so the poll above sees a SIGINT within a few waves
         // while the pipelines still overlap
-        if (interrupt && wave >= (uint64_t)pipes) CK(cudaEventSynchronize(ctx->ps[pi].resolved));
+        if (interrupt && ctx->ps[pi].used) CK(cudaEventSynchronize(ctx->ps[pi].resolved));
         if (depth == 0) {
             // raytrace(depth_left = 0) returns 0 (raytracer.odin:433): count the samples, add nothing
             CK(cudaMemsetAsync(ctx->ps[0].st_c, 0, (size_t)(nb * npix) * 16, ctx->stream));
             k_resolve<<<ctx->shade_grid, 256, 0, ctx->stream>>>(p, ctx->ps[0].st_c, d_accum, d_first, d_last,
                                                                 d_first && done == 0, d_last && done + nb == n_samples);
             ctx->launches++;
-        } else if (launch_wave(ctx, ctx->ps[pi], st, pipes > 1 ? prev : nullptr, p, d_accum, d_first, d_last,
-                               d_first && done == 0, d_last != nullptr)) {
-            return 1;
+        } else {
+            if (launch_wave(ctx, ctx->ps[pi], st, pipes > 1 ? ctx->last_resolved : nullptr, p, d_accum, d_first, d_last,
+                            d_first && done == 0, d_last != nullptr))
+                return 1;
+            ctx->last_resolved = ctx->ps[pi].resolved;
+            ctx->ps[pi].used = true;
         }
-        prev = ctx->ps[pi].resolved;
         done += nb;
-        wave++;
+        ctx->wave_seq++;
     }
-    for (int i = 1; i < pipes; i++) {
-        CK(cudaEventRecord(ctx->ev_join[i], ctx->aux_stream[i]));
-        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[i], 0));
+    if (chain) {
+        if (pipes > 1 && done > 0) { ctx->pipes_busy = true; ctx->chain_pipes = pipes; }
+    } else {
+        for (int i = 1; i < pipes; i++) {
+            CK(cudaEventRecord(ctx->ev_join[i], ctx->aux_stream[i]));
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[i], 0));
+        }
+        ctx->last_resolved = nullptr;
+        CK(cudaEventRecord(ctx->ev1, ctx->stream));
     }
-    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->last_done = done;
     if (done_out) *done_out = done;
     return 0;
 }
@@ -601,6 +667,31 @@ int pack_and_merge(ort_ctx* ctx, const float* accum, const float* first, const f
         }
     });
     if (pt) pt->mark("merge");
+    return 0;
+}
+
+// Second buffer of the frame: a device-to-device copy of the accumulators as of everything enqueued so far.
+// Preview / fetch work on it from the side stream while the pipelines go on accumulating.
+int frame_snapshot(ort_ctx* ctx) {
+    const size_t npix = (size_t)ctx->frame_w * ctx->frame_h;
+    if (join_pipes(ctx)) return 1;
+    if (!ctx->side_stream) {
+        CK(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ctx->snap_ev, cudaEventDisableTiming));
+    }
+    // (the previous snapshot's readers have finished: preview / fetch synchronise the side stream before returning)
+    CK(cudaMemcpyAsync(ctx->frame + 14 * npix, ctx->frame, npix * 14 * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaEventRecord(ctx->snap_ev, ctx->stream));
+    ctx->frame_snapshot_valid = true;
+    ctx->need_fork = true;
+    return 0;
+}
+int ensure_side(ort_ctx* ctx, size_t bytes) {
+    if (ctx->side_bytes >= bytes) return 0;
+    if (ctx->side_buf) { CK(cudaStreamSynchronize(ctx->side_stream)); cudaFree(ctx->side_buf); }
+    ctx->side_buf = nullptr; ctx->side_bytes = 0;
+    CK(cudaMalloc(&ctx->side_buf, bytes));
+    ctx->side_bytes = bytes;
     return 0;
 }
 
@@ -634,21 +725,20 @@ int ort_create(ort_ctx** out, const ort_device_cfg* cfg) {
     c->capacity_cfg = cfg ? cfg->max_paths_in_flight : 0;
     c->host_threads = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
     if (const char* e2 = std::getenv("ORT_HOST_THREADS")) c->host_threads = std::max(1, std::atoi(e2));
+    c->max_path_bytes = cfg ? cfg->max_path_bytes : 0;
+    if (const char* e2 = std::getenv("ORT_OVERLAP")) c->overlap = std::atoi(e2);
+    if (const char* e2 = std::getenv("ORT_WAVE_PATHS")) c->capacity_cfg = std::atoll(e2);
+#ifdef ORT_TUNING
     if (const char* e2 = std::getenv("ORT_REFILL")) c->refill = std::atoi(e2);
     if (const char* e2 = std::getenv("ORT_INNER_MIN")) c->inner_min = std::atoi(e2);
-    if (const char* e2 = std::getenv("ORT_FUSE")) c->fuse = std::atoi(e2);
-    if (const char* e2 = std::getenv("ORT_BVH8")) c->bvh8 = std::atoi(e2);
     if (const char* e2 = std::getenv("ORT_TILED")) c->tiled = std::atoi(e2);
-    if (const char* e2 = std::getenv("ORT_EXP_CTAS")) {
-        c->exp_ctas = std::atoi(e2);
-        if (c->exp_ctas > 0) {
-            const int bytes = 200 * 1024 / c->exp_ctas - 17 * 1024;
-            cudaFuncSetAttribute(k_trace<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-            cudaFuncSetAttribute(k_trace<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-        }
+    if (const char* e2 = std::getenv("ORT_TILE")) {
+        int a_ = 2, b_ = 2, c_ = 8;
+        if (std::sscanf(e2, "%dx%dx%d", &a_, &b_, &c_) == 3 && a_ * b_ * c_ == 32) { c->tile_w = a_; c->tile_h = b_; c->tile_s = c_; }
     }
     if (const char* e2 = std::getenv("ORT_LIGHT_PREFILTER")) c->light_prefilter = std::atoi(e2);
     if (const char* e2 = std::getenv("ORT_BIN")) c->bin_octants = std::atoi(e2);
+#endif
     ctx = c;
     auto bail = [&](const char* what, cudaError_t err) {
         g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
@@ -665,26 +755,14 @@ int ort_create(ort_ctx** out, const ort_device_cfg* cfg) {
         cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming);
     }
     for (auto& P : c->ps) cudaEventCreateWithFlags(&P.resolved, cudaEventDisableTiming);
-    if (const char* e2 = std::getenv("ORT_OVERLAP")) c->overlap = std::atoi(e2);
-    if (const char* e2 = std::getenv("ORT_WAVE_PATHS")) c->capacity_cfg = std::atoll(e2);
     if ((e = cudaMalloc(&c->d_stats, 8 * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc", e);
     cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long));
     // persistent grids: as many CTAs as stay resident, a multiple of the SM count
     int occ = 0;
-#define ORT_OCC(Q, M, ...)                                                                     \
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<__VA_ARGS__>, TRACE_THREADS, 0); \
-    c->trace_grid[Q][M] = c->sm_count * std::max(occ, 1);
-    ORT_OCC(0, 0, true, false, false) ORT_OCC(0, 1, false, true, false) ORT_OCC(0, 2, true, true, false)
-    ORT_OCC(1, 0, true, false, true) ORT_OCC(1, 1, false, true, true) ORT_OCC(1, 2, true, true, true)
-#undef ORT_OCC
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<true, false, 2>, TRACE_THREADS, 0);
-    c->trace8x_grid[0] = c->sm_count * std::max(occ, 1);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<false, true, 2>, TRACE_THREADS, 0);
-    c->trace8x_grid[1] = c->sm_count * std::max(occ, 1);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace8<true>, TRACE_THREADS, 0);
-    c->trace8_grid[0] = c->sm_count * std::max(occ, 1);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace8<false>, TRACE_THREADS, 0);
-    c->trace8_grid[1] = c->sm_count * std::max(occ, 1);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<false>, TRACE_THREADS, 0);
+    c->trace_grid[0] = c->sm_count * std::max(occ, 1);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<true>, TRACE_THREADS, 0);
+    c->trace_grid[1] = c->sm_count * std::max(occ, 1);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shade, 256, 0);
     c->shade_grid = c->sm_count * std::max(occ, 1);
     *out = c;
@@ -705,6 +783,10 @@ void ort_destroy(ort_ctx* ctx) {
     }
     if (ctx->d_stats) cudaFree(ctx->d_stats);
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->frame) cudaFree(ctx->frame);
+    if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
+    if (ctx->side_buf) cudaFree(ctx->side_buf);
+    if (ctx->snap_ev) cudaEventDestroy(ctx->snap_ev);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->stage) cudaFreeHost(ctx->stage);
     for (auto& e : ctx->stage_ev) if (e) cudaEventDestroy(e);
@@ -729,6 +811,13 @@ int ort_set_profiling(ort_ctx* ctx, int32_t on) {
 
 int ort_upload_scene(ort_ctx* ctx, const ort_scene* sc) {
     if (!ctx) return 1;
+    return guarded(ctx, [&] { return upload_scene_impl(ctx, sc, nullptr); });
+}
+
+} // extern "C"
+
+namespace {
+int upload_scene_impl(ort_ctx* ctx, const ort_scene* sc, SharedWide* shared) {
     if (!sc) return fail(ctx, "ort_upload_scene: scene is NULL");
     Bind b(ctx->device);
     PhaseTimer pt("ort_upload_scene");
@@ -743,33 +832,19 @@ int ort_upload_scene(ort_ctx* ctx, const ort_scene* sc) {
     if ((uint64_t)sc->n_triangles + (uint64_t)sc->n_light_triangles >= (1u << 28))
         return fail(ctx, "ort_upload_scene: more than 2^28 traversal triangles");
     if ((sc->n_triangles > 0 && !sc->triangles) || (sc->n_light_triangles > 0 && !sc->light_triangles) ||
-        (sc->n_materials > 0 && !sc->materials) || (sc->n_textures > 0 && !sc->textures))
+        (sc->n_materials > 0 && !sc->materials) || (sc->n_textures > 0 && !sc->textures) ||
+        (sc->n_bvh_nodes > 0 && !sc->bvh) || (sc->n_light_bvh_nodes > 0 && !sc->light_bvh))
         return fail(ctx, "ort_upload_scene: NULL array with a non-zero count");
+    if (sc->n_bvh_nodes < 0 || sc->n_light_bvh_nodes < 0) return fail(ctx, "ort_upload_scene: negative count");
     const size_t nt = (size_t)sc->n_triangles, nlt = (size_t)sc->n_light_triangles;
 
-    // The wide-BVH re-emission (serial, top-down) runs on its own host thread while this thread
-    // builds and uploads the per-triangle records, which do not depend on it.
-    const char* why_scene = nullptr;
-    const char* why_light = nullptr;
-    bool ok_scene = false, ok_light = false, ok8 = false, ok8x = false;
-    std::thread wide_thread([&] {
-        ok_scene = build_wide_bvh(sc->bvh, sc->n_bvh_nodes, sc->n_triangles, &ctx->wide, &why_scene);
-        ok_light = build_wide_bvh(sc->light_bvh, sc->n_light_bvh_nodes, sc->n_light_triangles, &ctx->lwide, &why_light);
-        ok8x = false;
-        if (ctx->bvh8 == 2 && ok_scene && ok_light) {
-            const char* why8 = nullptr;
-            ok8x = build_wide8x_bvh(sc->bvh, sc->n_bvh_nodes, sc->n_triangles, &ctx->wide8x, &why8) &&
-                   build_wide8x_bvh(sc->light_bvh, sc->n_light_bvh_nodes, sc->n_light_triangles, &ctx->lwide8x, &why8) &&
-                   ctx->wide8x.max_stack <= MAX_STACK && ctx->lwide8x.max_stack <= MAX_STACK;
-        }
-        ok8 = false;
-        if (ctx->bvh8 == 1 && ok_scene && ok_light) {
-            const char* why8 = nullptr; // e.g. leaves larger than the reference's 4: stay on the 4-wide tree
-            ok8 = build_wide8_bvh(sc->bvh, sc->n_bvh_nodes, sc->n_triangles, &ctx->wide8, &why8) &&
-                  build_wide8_bvh(sc->light_bvh, sc->n_light_bvh_nodes, sc->n_light_triangles, &ctx->lwide8, &why8) &&
-                  ctx->wide8.depth <= MAX_STACK && ctx->lwide8.depth <= MAX_STACK;
-        }
-    });
+    // The wide-BVH re-emission runs on its own host thread while this thread builds and uploads the
+    // per-triangle records, which do not depend on it.  With several GPUs (ort_multi_upload_scene) the
+    // emission is done ONCE and shared: `shared` then carries the result and this call only waits for it.
+    SharedWide own;
+    SharedWide* sw = shared ? shared : &own;
+    std::thread wide_thread;
+    if (!shared) wide_thread = std::thread([&] { own.build(sc); });
     struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{wide_thread};
 
     ctx->cam = sc->cam;
@@ -882,19 +957,21 @@ int ort_upload_scene(ort_ctx* ctx, const ort_scene* sc) {
     pt.mark("textures");
 
     // nodes: scene BVH (root 0) followed by the light BVH, whose references are rebased
-    wide_thread.join();
+    if (shared) shared->wait(); else wide_thread.join();
     pt.mark("wait_wide_bvh");
-    if (!ok_scene) { cudaStreamSynchronize(ctx->stream); return fail(ctx, std::string("scene BVH: ") + why_scene); }
-    if (!ok_light) { cudaStreamSynchronize(ctx->stream); return fail(ctx, std::string("light BVH: ") + why_light); }
-    if (ctx->wide.max_stack > MAX_STACK || ctx->lwide.max_stack > MAX_STACK) {
+    if (!sw->ok_scene) { cudaStreamSynchronize(ctx->stream); return fail(ctx, std::string("scene BVH: ") + sw->why_scene); }
+    if (!sw->ok_light) { cudaStreamSynchronize(ctx->stream); return fail(ctx, std::string("light BVH: ") + sw->why_light); }
+    const WideBVH& wide = sw->wide;
+    const WideBVH& lwide = sw->lwide;
+    if (wide.max_stack > MAX_STACK || lwide.max_stack > MAX_STACK) {
         cudaStreamSynchronize(ctx->stream);
-        return fail(ctx, "BVH too deep for the traversal stack (worst case " + std::to_string(ctx->wide.max_stack) + " > " +
+        return fail(ctx, "BVH too deep for the traversal stack (worst case " + std::to_string(wide.max_stack) + " > " +
                              std::to_string(MAX_STACK) + ")");
     }
     {
-        const size_t ns = ctx->wide.nodes.size(), nl = ctx->lwide.nodes.size();
+        const size_t ns = wide.nodes.size(), nl = lwide.nodes.size();
         auto light_node = [&](size_t i) {
-            WideNode w = ctx->lwide.nodes[i];
+            WideNode w = lwide.nodes[i];
             for (int k = 0; k < 4; k++) {
                 if (w.child[k] == WIDE_EMPTY) continue;
                 if (w.child[k] >= 0) w.child[k] += (int32_t)ns;
@@ -905,99 +982,22 @@ int ort_upload_scene(ort_ctx* ctx, const ort_scene* sc) {
             }
             return w;
         };
-        // node encoding: f32 planes by default.  The 8-bit encoding (QuantNode) halves the node
-        // traffic but its decode ALU cancels the gain on every scene measured so far (C2, C4, C5:
-        // profiles/r1_traversal_variants.md), so it is opt-in: ORT_QUANT=1
-        ctx->quant = false;
-        if (const char* e2 = std::getenv("ORT_QUANT")) ctx->quant = std::atoi(e2) != 0;
-        if (ctx->quant) {
-            std::vector<WideNode> nodes(ns + nl);
-            std::memcpy(nodes.data(), ctx->wide.nodes.data(), ns * sizeof(WideNode));
-            for (size_t i = 0; i < nl; i++) nodes[ns + i] = light_node(i);
-            if (scene_buffer(ctx, ort_ctx::SB_NODES, nodes.size() * sizeof(QuantNode), &d)) return 1;
-            if (staged_upload(ctx, d, nodes.size(), sizeof(QuantNode), 4096,
-                              [&](size_t f, size_t c, void* o) { quantize_wide_nodes(nodes.data() + f, c, (QuantNode*)o); }))
-                return 1;
-            CK(cudaStreamSynchronize(ctx->stream)); // `nodes` dies at the end of this block
-        } else {
-            if (scene_buffer(ctx, ort_ctx::SB_NODES, (ns + nl) * sizeof(WideNode), &d)) return 1;
-            if (staged_upload(ctx, d, ns, sizeof(WideNode), 8192,
-                              [&](size_t f, size_t c, void* o) { std::memcpy(o, ctx->wide.nodes.data() + f, c * sizeof(WideNode)); }))
-                return 1;
-            if (staged_upload(ctx, (char*)d + ns * sizeof(WideNode), nl, sizeof(WideNode), 8192, [&](size_t f, size_t c, void* o) {
-                    for (size_t i = 0; i < c; i++) ((WideNode*)o)[i] = light_node(f + i);
-                }))
-                return 1;
-        }
+        if (scene_buffer(ctx, ort_ctx::SB_NODES, (ns + nl) * sizeof(WideNode), &d)) return 1;
+        if (staged_upload(ctx, d, ns, sizeof(WideNode), 8192,
+                          [&](size_t f, size_t c, void* o) { std::memcpy(o, wide.nodes.data() + f, c * sizeof(WideNode)); }))
+            return 1;
+        if (staged_upload(ctx, (char*)d + ns * sizeof(WideNode), nl, sizeof(WideNode), 8192, [&](size_t f, size_t c, void* o) {
+                for (size_t i = 0; i < c; i++) ((WideNode*)o)[i] = light_node(f + i);
+            }))
+            return 1;
         sd.nodes = (const float4*)d;
         sd.light_root = (int32_t)ns;
     }
-    ctx->use8x = ok8x && !ctx->quant;
-    if (ctx->use8x) {
-        // exact-order 8-wide tree: scene nodes, then the light nodes with rebased references
-        const size_t ns8 = ctx->wide8x.nodes.size(), nl8 = ctx->lwide8x.nodes.size();
-        if (scene_buffer(ctx, ort_ctx::SB_NODES8X, (ns8 + nl8) * sizeof(Wide8xNode), &d)) return 1;
-        sd.nodes8x = (const float4*)d;
-        sd.light_root8x = (int32_t)ns8;
-        if (staged_upload(ctx, d, ns8, sizeof(Wide8xNode), 4096,
-                          [&](size_t f, size_t c, void* o) { std::memcpy(o, ctx->wide8x.nodes.data() + f, c * sizeof(Wide8xNode)); }))
-            return 1;
-        if (staged_upload(ctx, (char*)d + ns8 * sizeof(Wide8xNode), nl8, sizeof(Wide8xNode), 4096, [&](size_t f, size_t c, void* o) {
-                for (size_t i = 0; i < c; i++) {
-                    Wide8xNode w = ctx->lwide8x.nodes[f + i];
-                    for (int k = 0; k < 8; k++) {
-                        if (w.child[k] == WIDE_EMPTY) continue;
-                        if (w.child[k] >= 0) w.child[k] += (int32_t)ns8;
-                        else {
-                            const uint32_t code = (uint32_t)~w.child[k];
-                            w.child[k] = ~(int32_t)((((code >> 3) + (uint32_t)sc->n_triangles) << 3) | (code & 7u));
-                        }
-                    }
-                    ((Wide8xNode*)o)[i] = w;
-                }
-            }))
-            return 1;
-    }
-    ctx->use8 = ok8 && !ctx->quant;
-    if (ctx->use8) {
-        // 8-wide tree: nodes (scene, then light with rebased references) and traversal-order triangle records
-        const size_t ns8 = ctx->wide8.nodes.size(), nl8 = ctx->lwide8.nodes.size();
-        if (scene_buffer(ctx, ort_ctx::SB_NODES8, (ns8 + nl8) * sizeof(Wide8Node), &d)) return 1;
-        sd.nodes8 = (const float4*)d;
-        sd.light_root8 = (int32_t)ns8;
-        if (staged_upload(ctx, d, ns8, sizeof(Wide8Node), 4096,
-                          [&](size_t f, size_t c, void* o) { std::memcpy(o, ctx->wide8.nodes.data() + f, c * sizeof(Wide8Node)); }))
-            return 1;
-        if (staged_upload(ctx, (char*)d + ns8 * sizeof(Wide8Node), nl8, sizeof(Wide8Node), 4096, [&](size_t f, size_t c, void* o) {
-                for (size_t i = 0; i < c; i++) {
-                    Wide8Node w = ctx->lwide8.nodes[f + i];
-                    w.child_base += (uint32_t)ns8;
-                    w.tri_base += (uint32_t)nt;
-                    ((Wide8Node*)o)[i] = w;
-                }
-            }))
-            return 1;
-        if (scene_buffer(ctx, ort_ctx::SB_TRIS8, (nt + nlt) * sizeof(TriIsect), &d)) return 1;
-        sd.tris8 = (const float4*)d;
-        auto fill8 = [&](const ort_triangle* tris, const std::vector<uint32_t>& order, uint32_t id_base) {
-            return [=, &order](size_t f, size_t c, void* o) {
-                TriIsect* rec = (TriIsect*)o;
-                for (size_t i = 0; i < c; i++) {
-                    const uint32_t ref = order[f + i];
-                    make_isect_records(tris + ref, 1, rec + i);
-                    const uint32_t id = id_base + ref;
-                    std::memcpy(&rec[i].pad[0], &id, 4);
-                }
-            };
-        };
-        if (ctx->wide8.tri_order.size() != nt || ctx->lwide8.tri_order.size() != nlt) return fail(ctx, "8-wide BVH does not cover every triangle exactly once");
-        if (staged_upload(ctx, d, nt, sizeof(TriIsect), 4096, fill8(sc->triangles, ctx->wide8.tri_order, 0u))) return 1;
-        if (staged_upload(ctx, (char*)d + nt * sizeof(TriIsect), nlt, sizeof(TriIsect), 4096,
-                          fill8(sc->light_triangles, ctx->lwide8.tri_order, (uint32_t)nt)))
-            return 1;
-    }
     sd.n_lights = (int32_t)sc->n_light_triangles;
-    std::memcpy(sd.pad_scale, ctx->wide.max_abs, 12);
+    std::memcpy(sd.pad_scale, wide.max_abs, 12);
+    ctx->wide_nodes = (int64_t)wide.nodes.size(); ctx->wide_depth = wide.depth; ctx->wide_max_stack = wide.max_stack;
+    ctx->lwide_nodes = (int64_t)lwide.nodes.size();
+    ctx->ref_stack_need = sw->ref_stack_need;
     CK(cudaStreamSynchronize(ctx->stream));
     pt.mark("nodes+drain");
     // recycle what the new scene does not use (only happens when the scene's shape changed)
@@ -1012,13 +1012,16 @@ int ort_upload_scene(ort_ctx* ctx, const ort_scene* sc) {
     ctx->has_scene = true;
     return 0;
 }
+} // namespace
+
+extern "C" {
 
 int ort_render_device(ort_ctx* ctx, uint32_t w, uint32_t h, int32_t ray_depth, uint64_t first_sample,
                       uint64_t n_samples, float* d_accum) {
     if (!ctx) return 1;
     if (!d_accum) return fail(ctx, "ort_render_device: d_accum is NULL");
     Bind b(ctx->device);
-    return render_impl(ctx, w, h, ray_depth, first_sample, n_samples, d_accum, nullptr, nullptr, nullptr, nullptr);
+    return guarded(ctx, [&] { return render_impl(ctx, w, h, ray_depth, first_sample, n_samples, d_accum, nullptr, nullptr, nullptr, nullptr); });
 }
 
 int ort_render(ort_ctx* ctx, uint32_t w, uint32_t h, int32_t ray_depth, uint64_t first_sample, uint64_t n_samples,
@@ -1026,6 +1029,7 @@ int ort_render(ort_ctx* ctx, uint32_t w, uint32_t h, int32_t ray_depth, uint64_t
     if (!ctx) return 1;
     if (!out) return fail(ctx, "ort_render: out is NULL");
     Bind b(ctx->device);
+    return guarded(ctx, [&]() -> int {
     const size_t npix = (size_t)w * h;
     // planes: 8 accum + 3 first + 3 last, then the packed Sample_Stats
     if (ensure_scratch(ctx, npix * (14 * 4 + 52))) return 1;
@@ -1040,6 +1044,175 @@ int ort_render(ort_ctx* ctx, uint32_t w, uint32_t h, int32_t ray_depth, uint64_t
     pt.mark("enqueue");
     const int rc = pack_and_merge(ctx, accum, first, last, npix, packed, out, &pt);
     return rc;
+    });
+}
+
+uint64_t ort_last_render_samples(const ort_ctx* ctx) { return ctx ? ctx->last_done : 0; }
+
+// ---- device-resident frame ---------------------------------------------------------------------------
+int ort_frame_begin(ort_ctx* ctx, uint32_t w, uint32_t h) {
+    if (!ctx) return 1;
+    if (w == 0 || h == 0) return fail(ctx, "ort_frame_begin: width and height must be non-zero");
+    Bind b(ctx->device);
+    return guarded(ctx, [&]() -> int {
+        if (join_pipes(ctx)) return 1;
+        const size_t npix = (size_t)w * h, bytes = npix * 14 * 4;
+        if (ctx->frame_bytes < 2 * bytes) { // accumulators + their snapshot
+            CK(cudaStreamSynchronize(ctx->stream));
+            if (ctx->frame) cudaFree(ctx->frame);
+            ctx->frame = nullptr; ctx->frame_bytes = 0;
+            CK(cudaMalloc(&ctx->frame, 2 * bytes));
+            ctx->frame_bytes = 2 * bytes;
+        }
+        CK(cudaMemsetAsync(ctx->frame, 0, bytes, ctx->stream));
+        ctx->frame_w = w; ctx->frame_h = h;
+        ctx->frame_has_first = false;
+        ctx->frame_snapshot_valid = false;
+        ctx->need_fork = true;
+        return 0;
+    });
+}
+
+int ort_frame_end(ort_ctx* ctx) {
+    if (!ctx) return 1;
+    Bind b(ctx->device);
+    return guarded(ctx, [&]() -> int {
+        if (join_pipes(ctx)) return 1;
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->side_stream) CK(cudaStreamSynchronize(ctx->side_stream));
+        if (ctx->frame) cudaFree(ctx->frame);
+        ctx->frame = nullptr; ctx->frame_bytes = 0; ctx->frame_w = ctx->frame_h = 0;
+        return 0;
+    });
+}
+
+int ort_frame_load(ort_ctx* ctx, const ort_sample_stats* in) {
+    if (!ctx) return 1;
+    if (!ctx->frame_w) return fail(ctx, "ort_frame_load: no frame (ort_frame_begin)");
+    if (!in) return fail(ctx, "ort_frame_load: in is NULL");
+    Bind b(ctx->device);
+    return guarded(ctx, [&]() -> int {
+        const size_t npix = (size_t)ctx->frame_w * ctx->frame_h;
+        if (join_pipes(ctx)) return 1;
+        if (ensure_scratch(ctx, npix * 52)) return 1;
+        CK(cudaMemcpyAsync(ctx->scratch, in, npix * 52, cudaMemcpyHostToDevice, ctx->stream));
+        k_unpack_stats<<<ctx->shade_grid, 256, 0, ctx->stream>>>((const uint32_t*)ctx->scratch, (uint32_t)npix, ctx->frame,
+                                                                 ctx->frame + 8 * npix, ctx->frame + 11 * npix);
+        ctx->launches++;
+        CK(cudaStreamSynchronize(ctx->stream)); // `in` is the caller's pageable memory
+        ctx->frame_has_first = in[0].count > 0; // whole-frame rendering: every pixel holds the same count
+        ctx->need_fork = true;
+        return 0;
+    });
+}
+
+int ort_frame_render(ort_ctx* ctx, int32_t ray_depth, uint64_t first_sample, uint64_t n_samples,
+                     const volatile uint8_t* interrupt, uint64_t* done) {
+    if (!ctx) return 1;
+    if (!ctx->frame_w) return fail(ctx, "ort_frame_render: no frame (ort_frame_begin)");
+    Bind b(ctx->device);
+    return guarded(ctx, [&]() -> int {
+        const size_t npix = (size_t)ctx->frame_w * ctx->frame_h;
+        uint64_t d = 0;
+        if (render_impl(ctx, ctx->frame_w, ctx->frame_h, ray_depth, first_sample, n_samples, ctx->frame,
+                        ctx->frame_has_first ? nullptr : ctx->frame + 8 * npix, ctx->frame + 11 * npix, interrupt, &d, true))
+            return 1;
+        if (d > 0) ctx->frame_has_first = true;
+        if (done) *done = d;
+        return 0;
+    });
+}
+
+int ort_frame_wait(ort_ctx* ctx) {
+    if (!ctx) return 1;
+    Bind b(ctx->device);
+    return guarded(ctx, [&]() -> int {
+        if (join_pipes(ctx)) return 1;
+        CK(cudaStreamSynchronize(ctx->stream));
+        return 0;
+    });
+}
+
+int ort_frame_snapshot(ort_ctx* ctx) {
+    if (!ctx) return 1;
+    if (!ctx->frame_w) return fail(ctx, "ort_frame_snapshot: no frame (ort_frame_begin)");
+    Bind b(ctx->device);
+    return guarded(ctx, [&] { return frame_snapshot(ctx); });
+}
+
+int ort_frame_preview_rgb8(ort_ctx* ctx, uint8_t* out_rgb) {
+    if (!ctx) return 1;
+    if (!ctx->frame_w) return fail(ctx, "ort_frame_preview_rgb8: no frame (ort_frame_begin)");
+    if (!out_rgb) return fail(ctx, "ort_frame_preview_rgb8: out_rgb is NULL");
+    Bind b(ctx->device);
+    return guarded(ctx, [&]() -> int {
+        const size_t npix = (size_t)ctx->frame_w * ctx->frame_h;
+        if (!ctx->frame_snapshot_valid && frame_snapshot(ctx)) return 1;
+        // tone-map the snapshot on the side stream: the render pipelines keep running meanwhile
+        if (ensure_side(ctx, npix * 52)) return 1;
+        CK(cudaStreamWaitEvent(ctx->side_stream, ctx->snap_ev, 0));
+        k_tonemap<<<ctx->shade_grid, 256, 0, ctx->side_stream>>>(ctx->frame + 14 * npix, (uint32_t)npix, (uint8_t*)ctx->side_buf);
+        ctx->launches++;
+        CK(cudaMemcpyAsync(out_rgb, ctx->side_buf, npix * 3, cudaMemcpyDeviceToHost, ctx->side_stream));
+        CK(cudaStreamSynchronize(ctx->side_stream));
+        ctx->frame_snapshot_valid = false;
+        return 0;
+    });
+}
+
+int ort_frame_fetch(ort_ctx* ctx, ort_sample_stats* out) {
+    if (!ctx) return 1;
+    if (!ctx->frame_w) return fail(ctx, "ort_frame_fetch: no frame (ort_frame_begin)");
+    if (!out) return fail(ctx, "ort_frame_fetch: out is NULL");
+    Bind b(ctx->device);
+    return guarded(ctx, [&]() -> int {
+        const size_t npix = (size_t)ctx->frame_w * ctx->frame_h;
+        if (frame_snapshot(ctx)) return 1;
+        if (ensure_side(ctx, npix * 52)) return 1;
+        const float* snap = ctx->frame + 14 * npix;
+        CK(cudaStreamWaitEvent(ctx->side_stream, ctx->snap_ev, 0));
+        k_pack_stats<<<ctx->shade_grid, 256, 0, ctx->side_stream>>>(snap, snap + 8 * npix, snap + 11 * npix, (uint32_t)npix, (uint32_t*)ctx->side_buf);
+        ctx->launches++;
+        CK(cudaMemcpyAsync(out, ctx->side_buf, npix * 52, cudaMemcpyDeviceToHost, ctx->side_stream));
+        CK(cudaStreamSynchronize(ctx->side_stream));
+        ctx->frame_snapshot_valid = false;
+        return 0;
+    });
+}
+
+int ort_probe_shading(ort_ctx* ctx, int32_t kind, const float* in, int64_t n, float* out) {
+    if (!ctx) return 1;
+    if (!ctx->has_scene) return fail(ctx, "ort_upload_scene has not been called");
+    if (kind < 0 || kind > 7 || n < 0 || n > (1 << 24) || (n > 0 && (!in || !out))) return fail(ctx, "ort_probe_shading: bad arguments");
+    if (kind == ORT_PROBE_ENV && !ctx->sd.has_env) return fail(ctx, "ort_probe_shading: the scene has no environment map");
+    if (n == 0) return 0;
+    Bind b(ctx->device);
+    return guarded(ctx, [&]() -> int {
+        const size_t ni = (size_t)probe_in_floats(kind), no = (size_t)probe_out_floats(kind);
+        if (ensure_scratch(ctx, (size_t)n * (ni + no) * 4)) return 1;
+        float* d_in = ctx->scratch;
+        float* d_out = ctx->scratch + (size_t)n * ni;
+        CK(cudaMemcpyAsync(d_in, in, (size_t)n * ni * 4, cudaMemcpyHostToDevice, ctx->stream));
+        const float* lsum = nullptr;
+        if (kind == ORT_PROBE_PDF && ctx->sd.n_lights > 0) {
+            // pdf's light term: the light-BVH all-hit sum of (pos, out_d), by the same k_trace<true> render uses
+            if (join_pipes(ctx)) return 1;
+            if (ensure_paths(ctx, n)) return 1;
+            if (ensure_counters(ctx, 1)) return 1;
+            auto& P = ctx->ps[0];
+            CK(cudaMemsetAsync(P.counters, 0, sizeof(uint32_t) * 8, ctx->stream));
+            k_probe_pack<<<ctx->shade_grid, 256, 0, ctx->stream>>>(d_in, (uint32_t)n, P.qo[0], P.qd[0], P.counters);
+            launch_trace(ctx, P, ctx->stream, P.qo[0], P.qd[0], P.counters, P.counters + 1, 1);
+            ctx->launches++;
+            lsum = P.lsum;
+        }
+        k_probe<<<ctx->shade_grid, 256, 0, ctx->stream>>>(ctx->sd, kind, d_in, (uint32_t)n, d_out, lsum);
+        ctx->launches++;
+        CK(cudaMemcpyAsync(out, d_out, (size_t)n * no * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaGetLastError());
+        return 0;
+    });
 }
 
 int ort_unpack_accum(ort_ctx* ctx, uint32_t w, uint32_t h, const float* d_accum, ort_sample_stats* out) {
@@ -1225,9 +1398,11 @@ int ort_get_stats(ort_ctx* ctx, ort_stats* out) {
     if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->ms_render = ms; else cudaGetLastError();
     out->render_ms = ctx->ms_render;
     out->trace_ms = ctx->ms_trace; out->light_ms = ctx->ms_light; out->shade_ms = ctx->ms_shade; out->other_ms = ctx->ms_other;
-    out->wide_nodes = (int64_t)ctx->wide.nodes.size();
-    out->wide_depth = ctx->wide.depth;
-    out->light_wide_nodes = (int64_t)ctx->lwide.nodes.size();
+    out->wide_nodes = ctx->wide_nodes;
+    out->wide_depth = ctx->wide_depth;
+    out->light_wide_nodes = ctx->lwide_nodes;
+    out->wide_max_stack = ctx->wide_max_stack;
+    out->reference_stack_need = ctx->ref_stack_need;
     out->device_bytes = ctx->scene_bytes + ctx->path_bytes;
     return 0;
 }
@@ -1245,12 +1420,20 @@ int ort_reset_stats(ort_ctx* ctx) {
 } // extern "C"
 
 // =================================================================================================
-// Several GPUs from one process: sample-index split + one peer-memory reduce per call.
+// Several GPUs from one process: sample-index split + one peer-memory reduce per frame.
 // =================================================================================================
 struct ort_multi {
     std::vector<ort_ctx*> ctx;
     std::vector<char> peer; // devices[0] can dereference ctx[g]'s memory directly
     std::string err;
+    uint64_t last_done = 0;
+    // device-resident frame
+    uint32_t fw = 0, fh = 0;
+    int last_g = 0;                  // GPU that rendered the highest sample block of the latest call
+    bool snapshot_valid = false;
+    cudaStream_t rstream = nullptr;  // reduce / preview / fetch stream on devices[0]
+    float* rbuf = nullptr;           // devices[0]: reduced accumulators (8 planes) + last (3 planes) + staging (8 planes)
+    size_t rbuf_bytes = 0;
 };
 
 namespace {
@@ -1259,17 +1442,119 @@ thread_local std::string g_multi_create_error;
 struct PeerPtrs {
     const float* p[16];
 };
-// dst[i] += sum over peers; 7 planes (total, total_squared, count) of npix floats each.
-__global__ void k_reduce_peers(float* __restrict__ dst, const PeerPtrs peers, const int n_peers, const size_t n) {
+// dst[i] = (accumulate ? dst[i] : 0) + sum over the sources; 8 planes (total, total_squared, count_lo, count_hi)
+// of npix floats each.  Sources on other GPUs are read straight through NVLink peer memory.
+__global__ void k_reduce_peers(float* __restrict__ dst, const PeerPtrs src, const int n_src, const size_t n, const int accumulate) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        float acc = dst[i];
-        for (int k = 0; k < n_peers; k++) acc += peers.p[k][i]; // NVLink peer loads (or the local staging copy)
+        float acc = accumulate ? dst[i] : 0.0f;
+        for (int k = 0; k < n_src; k++) acc += src.p[k][i];
         dst[i] = acc;
     }
 }
 int mfail(ort_multi* m, const std::string& msg) {
     if (m) m->err = msg; else g_multi_create_error = msg;
     return 1;
+}
+template <typename F>
+int mguarded(ort_multi* m, F f) {
+    try {
+        return f();
+    } catch (const std::exception& e) {
+        return mfail(m, std::string("exception: ") + e.what());
+    } catch (...) {
+        return mfail(m, "unknown C++ exception");
+    }
+}
+// contiguous sample blocks, sizes differ by at most one
+void split_samples(uint64_t first_sample, uint64_t n_samples, int G, std::vector<uint64_t>* first, std::vector<uint64_t>* cnt) {
+    first->assign((size_t)G, 0); cnt->assign((size_t)G, 0);
+    const uint64_t base = n_samples / (uint64_t)G, rem = n_samples % (uint64_t)G;
+    uint64_t f = first_sample;
+    for (int g = 0; g < G; g++) { (*cnt)[g] = base + ((uint64_t)g < rem ? 1 : 0); (*first)[g] = f; f += (*cnt)[g]; }
+}
+// fn(g) on one host thread per GPU; returns the first failing GPU's index or -1
+template <typename F>
+int per_gpu(ort_multi* m, F fn) {
+    const int G = (int)m->ctx.size();
+    std::vector<int> rc((size_t)G, 0);
+    auto run = [&](int g) {
+        try { rc[g] = fn(g); } catch (const std::exception& e) { rc[g] = fail(m->ctx[g], std::string("exception: ") + e.what()); }
+        catch (...) { rc[g] = fail(m->ctx[g], "unknown C++ exception"); }
+    };
+    std::vector<std::thread> pool;
+    for (int g = 1; g < G; g++) pool.emplace_back(run, g);
+    run(0);
+    for (auto& t : pool) t.join();
+    for (int g = 0; g < G; g++) if (rc[g]) return g;
+    return -1;
+}
+int mfail_gpu(ort_multi* m, int g) { return mfail(m, "device " + std::to_string(m->ctx[g]->device) + ": " + ort_last_error(m->ctx[g])); }
+
+// devices[0]: dst (8 planes) = sum over g of src_of(g) (each GPU's 8 accumulator planes), on stream st.
+template <typename SrcOf>
+int reduce_to_dev0(ort_multi* m, cudaStream_t st, float* dst, float* staging, size_t npix, const std::vector<char>& take, SrcOf src_of) {
+    ort_ctx* ctx = m->ctx[0];
+    const int G = (int)m->ctx.size();
+    PeerPtrs pp{};
+    int np = 0;
+    for (int g = 0; g < G; g++)
+        if (take[g] && m->peer[g]) pp.p[np++] = src_of(g);
+    k_reduce_peers<<<ctx->shade_grid, 256, 0, st>>>(dst, pp, np, npix * 8, 0);
+    ctx->launches++;
+    for (int g = 1; g < G; g++) { // no peer access: stage, add, repeat
+        if (!take[g] || m->peer[g]) continue;
+        CK(cudaMemcpyPeerAsync(staging, ctx->device, src_of(g), m->ctx[g]->device, npix * 8 * 4, st));
+        PeerPtrs one{};
+        one.p[0] = staging;
+        k_reduce_peers<<<ctx->shade_grid, 256, 0, st>>>(dst, one, 1, npix * 8, 1);
+        ctx->launches++;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+int ensure_rbuf(ort_multi* m, size_t npix) {
+    ort_ctx* ctx = m->ctx[0];
+    const size_t bytes = npix * (8 + 3 + 3 + 8) * 4;
+    if (!m->rstream) CK(cudaStreamCreateWithFlags(&m->rstream, cudaStreamNonBlocking));
+    if (m->rbuf_bytes >= bytes) return 0;
+    if (m->rbuf) { CK(cudaStreamSynchronize(m->rstream)); cudaFree(m->rbuf); }
+    m->rbuf = nullptr; m->rbuf_bytes = 0;
+    CK(cudaMalloc(&m->rbuf, bytes));
+    m->rbuf_bytes = bytes;
+    return 0;
+}
+// Snapshot every GPU's frame and start the peer reduce on devices[0]'s side stream; returns without waiting.
+int multi_snapshot(ort_multi* m) {
+    const int G = (int)m->ctx.size();
+    const size_t npix = (size_t)m->fw * m->fh;
+    for (int g = 0; g < G; g++) {
+        ort_ctx* ctx = m->ctx[g];
+        Bind b(ctx->device);
+        if (frame_snapshot(ctx)) return mfail_gpu(m, g);
+    }
+    ort_ctx* ctx = m->ctx[0];
+    Bind b(ctx->device);
+    auto body = [&]() -> int {
+    if (ensure_rbuf(m, npix)) return 1;
+    for (int g = 0; g < G; g++) CK(cudaStreamWaitEvent(m->rstream, m->ctx[g]->snap_ev, 0));
+    float* red = m->rbuf;
+    float* firstp = red + 8 * npix;
+    float* lastp = firstp + 3 * npix;
+    float* staging = lastp + 3 * npix;
+    std::vector<char> take((size_t)G, 1);
+    if (reduce_to_dev0(m, m->rstream, red, staging, npix, take, [&](int g) { return (const float*)(m->ctx[g]->frame + 14 * npix); }))
+        return 1;
+    // first: GPU 0 rendered the frame's first sample; last: the GPU holding the highest block of the latest call
+    CK(cudaMemcpyAsync(firstp, m->ctx[0]->frame + 14 * npix + 8 * npix, npix * 3 * 4, cudaMemcpyDeviceToDevice, m->rstream));
+    const int lg = m->last_g;
+    if (lg == 0) CK(cudaMemcpyAsync(lastp, m->ctx[0]->frame + 14 * npix + 11 * npix, npix * 3 * 4, cudaMemcpyDeviceToDevice, m->rstream));
+    else CK(cudaMemcpyPeerAsync(lastp, ctx->device, m->ctx[lg]->frame + 14 * npix + 11 * npix, m->ctx[lg]->device, npix * 3 * 4, m->rstream));
+    return 0;
+    };
+    if (body()) return mfail_gpu(m, 0);
+    m->snapshot_valid = true;
+    for (int g = 0; g < G; g++) m->ctx[g]->frame_snapshot_valid = false; // consumed by the reduce above
+    return 0;
 }
 } // namespace
 
@@ -1279,6 +1564,11 @@ const char* ort_multi_last_error(const ort_multi* m) { return m ? m->err.c_str()
 
 void ort_multi_destroy(ort_multi* m) {
     if (!m) return;
+    if (!m->ctx.empty()) {
+        Bind b(m->ctx[0]->device);
+        if (m->rstream) { cudaStreamSynchronize(m->rstream); cudaStreamDestroy(m->rstream); }
+        if (m->rbuf) cudaFree(m->rbuf);
+    }
     for (ort_ctx* c : m->ctx) ort_destroy(c);
     delete m;
 }
@@ -1286,7 +1576,8 @@ void ort_multi_destroy(ort_multi* m) {
 int ort_multi_create(ort_multi** out, const int32_t* devices, int32_t n_devices, uint64_t seed) {
     if (!out || !devices || n_devices < 1 || n_devices > 16) return mfail(nullptr, "ort_multi_create: need 1..16 devices");
     *out = nullptr;
-    ort_multi* m = new ort_multi();
+    ort_multi* m = nullptr;
+    try { m = new ort_multi(); } catch (...) { return mfail(nullptr, "out of host memory"); }
     for (int g = 0; g < n_devices; g++) {
         ort_device_cfg cfg{};
         cfg.device = devices[g];
@@ -1316,53 +1607,51 @@ int ort_multi_create(ort_multi** out, const int32_t* devices, int32_t n_devices,
     return 0;
 }
 
+// All GPUs upload concurrently (one host thread each); the wide-BVH re-emission is done once and shared.
 int ort_multi_upload_scene(ort_multi* m, const ort_scene* scene) {
     if (!m) return 1;
-    for (size_t g = 0; g < m->ctx.size(); g++)
-        if (ort_upload_scene(m->ctx[g], scene) != 0)
-            return mfail(m, "device " + std::to_string(m->ctx[g]->device) + ": " + ort_last_error(m->ctx[g]));
-    return 0;
+    if (!scene) return mfail(m, "ort_multi_upload_scene: scene is NULL");
+    return mguarded(m, [&]() -> int {
+        SharedWide shared;
+        const bool arrays_ok = (scene->n_bvh_nodes <= 0 || scene->bvh) && (scene->n_light_bvh_nodes <= 0 || scene->light_bvh);
+        std::thread builder([&] {
+            if (arrays_ok) shared.build(scene);
+            else { std::lock_guard<std::mutex> l(shared.mu); shared.ready = true; shared.cv.notify_all(); }
+        });
+        const int bad = per_gpu(m, [&](int g) { return upload_scene_impl(m->ctx[g], scene, &shared); });
+        builder.join();
+        return bad >= 0 ? mfail_gpu(m, bad) : 0;
+    });
 }
 
 int ort_multi_render(ort_multi* m, uint32_t w, uint32_t h, int32_t ray_depth, uint64_t first_sample,
                      uint64_t n_samples, ort_sample_stats* out, const volatile uint8_t* interrupt) {
     if (!m) return 1;
     if (!out) return mfail(m, "ort_multi_render: out is NULL");
+    return mguarded(m, [&]() -> int {
     const int G = (int)m->ctx.size();
     const size_t npix = (size_t)w * h;
-    // contiguous sample blocks, sizes differ by at most one
-    std::vector<uint64_t> first((size_t)G), cnt((size_t)G);
-    {
-        const uint64_t base = n_samples / (uint64_t)G, rem = n_samples % (uint64_t)G;
-        uint64_t f = first_sample;
-        for (int g = 0; g < G; g++) { cnt[g] = base + ((uint64_t)g < rem ? 1 : 0); first[g] = f; f += cnt[g]; }
-    }
-    int last_g = 0;
-    for (int g = 0; g < G; g++) if (cnt[g] > 0) last_g = g;
-    std::vector<int> rc((size_t)G, 0);
-    auto work = [&](int g) {
+    std::vector<uint64_t> first, cnt, done((size_t)G, 0);
+    split_samples(first_sample, n_samples, G, &first, &cnt);
+    const int bad = per_gpu(m, [&](int g) -> int {
         ort_ctx* ctx = m->ctx[g];
         Bind b(ctx->device);
-        auto body = [&]() -> int {
-            // planes: 8 accum + 3 first + 3 last (+ packed Sample_Stats and a staging area on device 0)
-            if (ensure_scratch(ctx, npix * (14 * 4 + 52) + (g == 0 ? npix * 7 * 4 : 0))) return 1;
-            float* accum = ctx->scratch;
-            CK(cudaMemsetAsync(accum, 0, npix * 14 * 4, ctx->stream));
-            if (cnt[g] > 0 &&
-                render_impl(ctx, w, h, ray_depth, first[g], cnt[g], accum, g == 0 ? accum + 8 * npix : nullptr,
-                            g == last_g ? accum + 11 * npix : nullptr, interrupt, nullptr))
-                return 1;
-            CK(cudaStreamSynchronize(ctx->stream));
-            return 0;
-        };
-        rc[g] = body();
-    };
-    std::vector<std::thread> pool;
-    for (int g = 1; g < G; g++) pool.emplace_back(work, g);
-    work(0);
-    for (auto& t : pool) t.join();
-    for (int g = 0; g < G; g++)
-        if (rc[g]) return mfail(m, "device " + std::to_string(m->ctx[g]->device) + ": " + ort_last_error(m->ctx[g]));
+        // planes: 8 accum + 3 first + 3 last (+ packed Sample_Stats and a staging area on device 0)
+        if (ensure_scratch(ctx, npix * (14 * 4 + 52) + (g == 0 ? npix * 8 * 4 : 0))) return 1;
+        float* accum = ctx->scratch;
+        CK(cudaMemsetAsync(accum, 0, npix * 14 * 4, ctx->stream));
+        if (cnt[g] > 0 && render_impl(ctx, w, h, ray_depth, first[g], cnt[g], accum, g == 0 ? accum + 8 * npix : nullptr,
+                                      accum + 11 * npix, interrupt, &done[g]))
+            return 1;
+        CK(cudaStreamSynchronize(ctx->stream));
+        return 0;
+    });
+    if (bad >= 0) return mfail_gpu(m, bad);
+    m->last_done = 0;
+    int last_g = 0; // `last` comes from the highest block that actually rendered something (interrupts)
+    std::vector<char> take((size_t)G, 0);
+    for (int g = 0; g < G; g++) { m->last_done += done[g]; if (done[g] > 0) { last_g = g; take[g] = 1; } }
+    take[0] = 1;
 
     ort_ctx* ctx = m->ctx[0];
     Bind b(ctx->device);
@@ -1371,24 +1660,23 @@ int ort_multi_render(ort_multi* m, uint32_t w, uint32_t h, int32_t ray_depth, ui
     float* lastp = firstp + 3 * npix;
     uint32_t* packed = (uint32_t*)(lastp + 3 * npix);
     float* staging = (float*)((char*)packed + npix * 52);
-    // the one reduce of the frame: devices[0] sums its peers' accumulators
-    PeerPtrs pp{};
-    int np = 0;
-    for (int g = 1; g < G; g++) {
-        if (cnt[g] == 0) continue;
-        if (m->peer[g]) {
-            pp.p[np++] = m->ctx[g]->scratch;
-        } else { // no peer access: stage, add, repeat
-            CK(cudaMemcpyPeerAsync(staging, ctx->device, m->ctx[g]->scratch, m->ctx[g]->device, npix * 7 * 4, ctx->stream));
+    // the one reduce of the frame: devices[0] sums its peers' accumulators into its own
+    {
+        PeerPtrs pp{};
+        int np = 0;
+        for (int g = 1; g < G; g++) {
+            if (!take[g]) continue;
+            if (m->peer[g]) { pp.p[np++] = m->ctx[g]->scratch; continue; }
+            CK(cudaMemcpyPeerAsync(staging, ctx->device, m->ctx[g]->scratch, m->ctx[g]->device, npix * 8 * 4, ctx->stream));
             PeerPtrs one{};
             one.p[0] = staging;
-            k_reduce_peers<<<ctx->shade_grid, 256, 0, ctx->stream>>>(accum, one, 1, npix * 7);
+            k_reduce_peers<<<ctx->shade_grid, 256, 0, ctx->stream>>>(accum, one, 1, npix * 8, 1);
             ctx->launches++;
         }
-    }
-    if (np > 0) {
-        k_reduce_peers<<<ctx->shade_grid, 256, 0, ctx->stream>>>(accum, pp, np, npix * 7);
-        ctx->launches++;
+        if (np > 0) {
+            k_reduce_peers<<<ctx->shade_grid, 256, 0, ctx->stream>>>(accum, pp, np, npix * 8, 1);
+            ctx->launches++;
+        }
     }
     if (last_g != 0)
         CK(cudaMemcpyPeerAsync(lastp, ctx->device, m->ctx[last_g]->scratch + 11 * npix, m->ctx[last_g]->device,
@@ -1396,6 +1684,110 @@ int ort_multi_render(ort_multi* m, uint32_t w, uint32_t h, int32_t ray_depth, ui
     CK(cudaGetLastError());
     if (pack_and_merge(ctx, accum, firstp, lastp, npix, packed, out)) return mfail(m, ort_last_error(ctx));
     return 0;
+    });
+}
+
+uint64_t ort_multi_last_render_samples(const ort_multi* m) { return m ? m->last_done : 0; }
+
+int ort_multi_frame_begin(ort_multi* m, uint32_t w, uint32_t h) {
+    if (!m) return 1;
+    return mguarded(m, [&]() -> int {
+        const int bad = per_gpu(m, [&](int g) { return ort_frame_begin(m->ctx[g], w, h); });
+        if (bad >= 0) return mfail_gpu(m, bad);
+        m->fw = w; m->fh = h; m->last_g = 0; m->snapshot_valid = false;
+        return 0;
+    });
+}
+
+int ort_multi_frame_end(ort_multi* m) {
+    if (!m) return 1;
+    return mguarded(m, [&]() -> int {
+        if (m->rstream) { Bind b(m->ctx[0]->device); cudaStreamSynchronize(m->rstream); }
+        const int bad = per_gpu(m, [&](int g) { return ort_frame_end(m->ctx[g]); });
+        m->fw = m->fh = 0;
+        return bad >= 0 ? mfail_gpu(m, bad) : 0;
+    });
+}
+
+// The loaded image goes to devices[0]; the other GPUs start from zero (their partial sums are added at fetch).
+int ort_multi_frame_load(ort_multi* m, const ort_sample_stats* in) {
+    if (!m) return 1;
+    if (!m->fw) return mfail(m, "ort_multi_frame_load: no frame (ort_multi_frame_begin)");
+    if (ort_frame_load(m->ctx[0], in)) return mfail_gpu(m, 0);
+    return 0;
+}
+
+int ort_multi_frame_render(ort_multi* m, int32_t ray_depth, uint64_t first_sample, uint64_t n_samples,
+                           const volatile uint8_t* interrupt, uint64_t* done_out) {
+    if (!m) return 1;
+    if (!m->fw) return mfail(m, "ort_multi_frame_render: no frame (ort_multi_frame_begin)");
+    return mguarded(m, [&]() -> int {
+        const int G = (int)m->ctx.size();
+        std::vector<uint64_t> first, cnt, done((size_t)G, 0);
+        split_samples(first_sample, n_samples, G, &first, &cnt);
+        const int bad = per_gpu(m, [&](int g) -> int {
+            return cnt[g] > 0 ? ort_frame_render(m->ctx[g], ray_depth, first[g], cnt[g], interrupt, &done[g]) : 0;
+        });
+        if (bad >= 0) return mfail_gpu(m, bad);
+        m->last_done = 0;
+        for (int g = 0; g < G; g++) { m->last_done += done[g]; if (done[g] > 0) m->last_g = g; } // ascending: ends on the highest block
+        if (done_out) *done_out = m->last_done;
+        return 0;
+    });
+}
+
+int ort_multi_frame_wait(ort_multi* m) {
+    if (!m) return 1;
+    return mguarded(m, [&]() -> int {
+        const int bad = per_gpu(m, [&](int g) { return ort_frame_wait(m->ctx[g]); });
+        return bad >= 0 ? mfail_gpu(m, bad) : 0;
+    });
+}
+
+int ort_multi_frame_snapshot(ort_multi* m) {
+    if (!m) return 1;
+    if (!m->fw) return mfail(m, "ort_multi_frame_snapshot: no frame (ort_multi_frame_begin)");
+    return mguarded(m, [&] { return multi_snapshot(m); });
+}
+
+int ort_multi_frame_preview_rgb8(ort_multi* m, uint8_t* out_rgb) {
+    if (!m) return 1;
+    if (!m->fw) return mfail(m, "ort_multi_frame_preview_rgb8: no frame (ort_multi_frame_begin)");
+    if (!out_rgb) return mfail(m, "ort_multi_frame_preview_rgb8: out_rgb is NULL");
+    return mguarded(m, [&]() -> int {
+        if (!m->snapshot_valid && multi_snapshot(m)) return 1;
+        ort_ctx* ctx = m->ctx[0];
+        Bind b(ctx->device);
+        const size_t npix = (size_t)m->fw * m->fh;
+        if (ensure_side(ctx, npix * 52)) return mfail_gpu(m, 0);
+        k_tonemap<<<ctx->shade_grid, 256, 0, m->rstream>>>(m->rbuf, (uint32_t)npix, (uint8_t*)ctx->side_buf);
+        ctx->launches++;
+        if (cudaMemcpyAsync(out_rgb, ctx->side_buf, npix * 3, cudaMemcpyDeviceToHost, m->rstream) != cudaSuccess ||
+            cudaStreamSynchronize(m->rstream) != cudaSuccess)
+            return mfail(m, std::string("preview: ") + cudaGetErrorString(cudaGetLastError()));
+        m->snapshot_valid = false;
+        return 0;
+    });
+}
+
+int ort_multi_frame_fetch(ort_multi* m, ort_sample_stats* out) {
+    if (!m) return 1;
+    if (!m->fw) return mfail(m, "ort_multi_frame_fetch: no frame (ort_multi_frame_begin)");
+    if (!out) return mfail(m, "ort_multi_frame_fetch: out is NULL");
+    return mguarded(m, [&]() -> int {
+        if (multi_snapshot(m)) return 1;
+        ort_ctx* ctx = m->ctx[0];
+        Bind b(ctx->device);
+        const size_t npix = (size_t)m->fw * m->fh;
+        if (ensure_side(ctx, npix * 52)) return mfail_gpu(m, 0);
+        k_pack_stats<<<ctx->shade_grid, 256, 0, m->rstream>>>(m->rbuf, m->rbuf + 8 * npix, m->rbuf + 11 * npix, (uint32_t)npix, (uint32_t*)ctx->side_buf);
+        ctx->launches++;
+        if (cudaMemcpyAsync(out, ctx->side_buf, npix * 52, cudaMemcpyDeviceToHost, m->rstream) != cudaSuccess ||
+            cudaStreamSynchronize(m->rstream) != cudaSuccess)
+            return mfail(m, std::string("fetch: ") + cudaGetErrorString(cudaGetLastError()));
+        m->snapshot_valid = false;
+        return 0;
+    });
 }
 
 int ort_multi_get_stats(ort_multi* m, ort_stats* out) {
@@ -1410,6 +1802,7 @@ int ort_multi_get_stats(ort_multi* m, ort_stats* out) {
         out->trace_ms = std::max(out->trace_ms, s.trace_ms); out->light_ms = std::max(out->light_ms, s.light_ms);
         out->shade_ms = std::max(out->shade_ms, s.shade_ms); out->other_ms = std::max(out->other_ms, s.other_ms);
         out->wide_nodes = s.wide_nodes; out->wide_depth = s.wide_depth; out->light_wide_nodes = s.light_wide_nodes;
+        out->wide_max_stack = s.wide_max_stack; out->reference_stack_need = s.reference_stack_need;
         out->device_bytes += s.device_bytes;
     }
     return 0;

@@ -3,6 +3,12 @@
 //   odinrt <input.gltf> [output.ppm|png] --width W --height H --ray-depth D --num-samples N
 //          [--env-map file.hdr] [--times T] [--continious] [--threads n]
 //          [--gpus 0,1,...] [--seed S] [--bvh host|device] [--checkpoint f] [--resume f] [--chunk spp]
+//          [--preview file.png|ppm] [--preview-every seconds] [--duration seconds]
+//
+// The accumulators live on the GPU(s) for the whole run (ort_frame_*): --continious enqueues chunks of
+// `--chunk` samples PER GPU back to back (default 64), the periodic preview is tone-mapped on the device
+// (3 bytes per pixel to the host, written by a background thread), and the 52-byte-per-pixel Sample_Stats
+// cross the bus once, at exit.  --duration stops a continuous run after that many seconds (like a SIGINT).
 //
 // read_gltf -> (width/height/fov/env-map overrides) -> finish_scene -> render_scene -> save_result,
 // with render_scene being the C ABI of libodinrt_b200.so (include/odinrt_b200.h).  Like the
@@ -17,6 +23,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "scene.hpp"
@@ -34,8 +41,9 @@ void on_sigint(int) { g_interrupt = 1; }
 double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 struct Args {
-    std::string input_file, output_file, env_map, gpus = "0", bvh = "host", checkpoint, resume;
-    long times = 0, threads = 0, width = 0, height = 0, ray_depth = 0, num_samples = 0, chunk = 16;
+    std::string input_file, output_file, env_map, gpus = "0", bvh = "host", checkpoint, resume, preview;
+    long times = 0, threads = 0, width = 0, height = 0, ray_depth = 0, num_samples = 0, chunk = 64;
+    double preview_every = 5.0, duration = 0.0;
     unsigned long long seed = 0;
     bool continious = false, debug = false;
 };
@@ -72,10 +80,14 @@ Args parse_args(int argc, char** argv) {
             else if (s == "checkpoint") a.checkpoint = value();
             else if (s == "resume") a.resume = value();
             else if (s == "chunk") a.chunk = num();
+            else if (s == "preview") a.preview = value();
+            else if (s == "preview-every" || s == "preview_every") a.preview_every = std::strtod(value().c_str(), nullptr);
+            else if (s == "duration") a.duration = std::strtod(value().c_str(), nullptr);
             else if (s == "help" || s == "h") {
                 std::printf("usage: odinrt <input.gltf> [output.ppm|png] --width W --height H --ray-depth D --num-samples N\n"
                             "       [--env-map f.hdr] [--times T] [--continious] [--threads n] [--gpus 0,1,..] [--seed S]\n"
-                            "       [--bvh host|device] [--checkpoint f] [--resume f] [--chunk spp]\n");
+                            "       [--bvh host|device] [--checkpoint f] [--resume f] [--chunk spp-per-gpu]\n"
+                            "       [--preview f.png] [--preview-every s] [--duration s]\n");
                 std::exit(0);
             } else die("unknown flag: --" + s);
         } else if (positional == 0) { a.input_file = s; positional++; }
@@ -154,32 +166,78 @@ int main(int argc, char** argv) {
         if (ort_multi_create(&multi, devices.data(), (int32_t)devices.size(), a.seed)) die(std::string("ort_multi_create: ") + ort_multi_last_error(nullptr));
         if (ort_multi_upload_scene(multi, &view)) die(std::string("ort_multi_upload_scene: ") + ort_multi_last_error(multi));
     }
-    auto render = [&](uint64_t first, uint64_t n, std::vector<ort_sample_stats>& px) {
-        const int rc = ctx ? ort_render(ctx, (uint32_t)a.width, (uint32_t)a.height, (int32_t)a.ray_depth, first, n, px.data(), &g_interrupt)
-                           : ort_multi_render(multi, (uint32_t)a.width, (uint32_t)a.height, (int32_t)a.ray_depth, first, n, px.data(), &g_interrupt);
-        if (rc) die(std::string("render: ") + (ctx ? ort_last_error(ctx) : ort_multi_last_error(multi)));
-    };
-
+    // the frame: accumulators stay in HBM until the end of the run
     const uint32_t w = (uint32_t)a.width, h = (uint32_t)a.height;
+    auto check = [&](int rc, const char* what) {
+        if (rc) die(std::string(what) + ": " + (ctx ? ort_last_error(ctx) : ort_multi_last_error(multi)));
+    };
+    auto frame_render = [&](uint64_t first, uint64_t n) -> uint64_t {
+        uint64_t done = 0;
+        check(ctx ? ort_frame_render(ctx, (int32_t)a.ray_depth, first, n, &g_interrupt, &done)
+                  : ort_multi_frame_render(multi, (int32_t)a.ray_depth, first, n, &g_interrupt, &done), "render");
+        return done;
+    };
+    auto frame_wait = [&] { check(ctx ? ort_frame_wait(ctx) : ort_multi_frame_wait(multi), "wait"); };
+    check(ctx ? ort_frame_begin(ctx, w, h) : ort_multi_frame_begin(multi, w, h), "frame_begin");
+
     std::vector<ort_sample_stats> pixels((size_t)w * h); // create_rendering_context: zeroed Sample_Stats
     uint64_t first = 0;
-    if (!a.resume.empty() && !load_checkpoint(a.resume, w, h, &first, &pixels))
-        die("checkpoint " + a.resume + " does not match a " + std::to_string(w) + "x" + std::to_string(h) + " Sample_Stats image");
+    if (!a.resume.empty()) {
+        if (!load_checkpoint(a.resume, w, h, &first, &pixels))
+            die("checkpoint " + a.resume + " does not match a " + std::to_string(w) + "x" + std::to_string(h) + " Sample_Stats image");
+        check(ctx ? ort_frame_load(ctx, pixels.data()) : ort_multi_frame_load(multi, pixels.data()), "frame_load");
+    }
 
     if (a.continious) { // samples = max(int): render until interrupted (main.odin:207)
-        const uint64_t start = first;
+        const uint64_t chunk = (uint64_t)std::max(1L, a.chunk) * devices.size(); // --chunk samples per GPU and call
+        uint64_t rendered = 0;
+        std::vector<uint8_t> rgb((size_t)w * h * 3), rgb_writing;
+        std::thread writer;
+        double host_blocked = 0; // time the render loop spent in preview calls (device keeps rendering meanwhile)
+        int previews = 0;
         t0 = now_s();
+        double next_preview = t0 + a.preview_every;
         while (!g_interrupt) {
-            render(first, (uint64_t)std::max(1L, a.chunk), pixels);
-            first += (uint64_t)std::max(1L, a.chunk);
+            rendered += frame_render(first, chunk);
+            first += chunk; // an interrupted call still consumes its index range: no sample index is ever reused
+            const double now = now_s();
+            if (a.duration > 0 && now - t0 >= a.duration) g_interrupt = 1;
+            if (!a.preview.empty() && now >= next_preview && !g_interrupt) {
+                // get_rgb_image on the device (output.odin:30-80): snapshot now, enqueue the next chunk, THEN wait
+                // for the 3-byte-per-pixel image — the GPUs never idle while the host reads or encodes it
+                check(ctx ? ort_frame_snapshot(ctx) : ort_multi_frame_snapshot(multi), "snapshot");
+                rendered += frame_render(first, chunk);
+                first += chunk;
+                const double tp = now_s();
+                check(ctx ? ort_frame_preview_rgb8(ctx, rgb.data()) : ort_multi_frame_preview_rgb8(multi, rgb.data()), "preview");
+                host_blocked += now_s() - tp;
+                if (writer.joinable()) writer.join();
+                rgb_writing = rgb;
+                writer = std::thread([&, path = a.preview] {
+                    std::string e;
+                    const bool png = path.size() > 4 && path.compare(path.size() - 4, 4, ".png") == 0;
+                    if (!(png ? orh::write_png(path, (int)w, (int)h, rgb_writing.data(), &e) : orh::write_ppm(path, (int)w, (int)h, rgb_writing.data(), &e)))
+                        std::fprintf(stderr, "preview: %s\n", e.c_str());
+                });
+                previews++;
+                next_preview = now_s() + a.preview_every;
+            }
         }
-        std::printf("Rendered %llu samples in %.2fs\n", (unsigned long long)(first - start), now_s() - t0);
+        frame_wait();
+        const double dt = now_s() - t0;
+        if (writer.joinable()) writer.join();
+        ort_stats st{};
+        if (ctx) ort_get_stats(ctx, &st); else ort_multi_get_stats(multi, &st);
+        std::printf("Rendered %llu samples in %.2fs\n", (unsigned long long)rendered, dt);
+        std::printf("%.1f Mrays/s sustained, %.1f Msamples/s, %d previews (host blocked %.1f ms in total)\n",
+                    (double)st.rays_closest / dt / 1e6, (double)st.paths / dt / 1e6, previews, host_blocked * 1e3);
     } else {
         const long trials = a.times > 0 ? a.times : 1;
         std::vector<double> timings;
         for (long trial = 0; trial < trials; trial++) { // render_scene (raytracer.odin:606-624): trials replay the same samples
             t0 = now_s();
-            render(first, (uint64_t)std::max(0L, a.num_samples), pixels);
+            frame_render(first, (uint64_t)std::max(0L, a.num_samples));
+            frame_wait();
             timings.push_back(now_s() - t0);
             std::printf("Trial %ld >>> Rendered in %.3fms\n", trial, timings.back() * 1e3);
         }
@@ -201,6 +259,10 @@ int main(int argc, char** argv) {
                         trials, mean * 1e3, sd * 1e3, ts.front() * 1e3, med * 1e3, ts.back() * 1e3);
         }
     }
+    // the one 52-byte-per-pixel transfer of the run
+    t0 = now_s();
+    check(ctx ? ort_frame_fetch(ctx, pixels.data()) : ort_multi_frame_fetch(multi, pixels.data()), "frame_fetch");
+    std::printf("Sample_Stats fetched in %.1fms\n", (now_s() - t0) * 1e3);
     if (!a.checkpoint.empty() && !save_checkpoint(a.checkpoint, w, h, first, pixels)) die("failed to write checkpoint " + a.checkpoint);
     if (!a.output_file.empty() && !orh::save_result(pixels.data(), (int)w, (int)h, a.output_file, &err)) die(err);
     if (ctx) ort_destroy(ctx);

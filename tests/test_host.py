@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert declared == set(cabi.ABI), "cabi.ABI and the header disagree"
-    assert lib.ort_abi_version() == 1
+    assert lib.ort_abi_version() == 2
 
 
 def test_struct_layouts_match_the_reference():
