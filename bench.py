@@ -1,24 +1,31 @@
 #!/usr/bin/env python
 """bench.py — Mrays/s of the path-tracing hot path on BASELINE.json's configs.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--config C2] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config C4] [--spp S] [--impl reference]
 
-A *step* is one pass of the hot path over one batch: `spp` samples of every pixel of the named
-config (default C2: generated ~100k-triangle instanced-sphere glTF, 1920x1080, ray-depth 8,
-256 spp — BASELINE.json configs[1]).  The scene replica is resident in HBM before the timed region.
+A *step* is one FRAME of the named config: `spp` samples of every pixel (default C4, the configuration
+BASELINE.json's target is quoted on: procedural 1 M-triangle scene, 1920x1080, ray-depth 10, 4096 spp —
+configs[3]).  The scene replica is resident in HBM before the timed region.  With N GPUs the frame's
+sample range is DIVIDED over the ranks (strong scaling: total work fixed, `multigpu.sample_partition`),
+every rank renders its block into device accumulators, and ONE NCCL reduce per frame combines them on
+rank 0 — inside the timed region.  --config C2 / C3 / C5 select the other BASELINE configs.
 
   value     whole-job Mrays/s (closest-hit cast_ray calls the reference would make / s / 1e6),
-            device-timed with CUDA events over exactly K steps, max over ranks.
-  e2e       the same metric through the public host call (ort_upload_scene + ort_render with HOST
-            buffers): scene H2D and Sample_Stats D2H inside the timed region.
-  roofline  dominant kernel k_trace: algorithmic bytes/ray (32 + 16 + 24*N_box +
-            36*N_tri, N_* from the oracle's duplicate-free traversal of the same BVH) x rays /
-            CUDA-event time of the k_trace launches of one step; peak = MEASURED_PEAKS.json hbm_gbs.
+            device-timed with CUDA events over exactly K frames, max over ranks.
+  e2e       the same metric through the public host calls with HOST buffers, per frame:
+            ort_upload_scene (scene H2D) + render + reduce + ONE host Sample_Stats image (D2H, 52 B/px) on
+            rank 0, wall clock, max over ranks.  N = 1: ort_render; N > 1: ort_render_device + the NCCL
+            reduce + ort_unpack_accum.
+  roofline  dominant kernel k_trace<closest>: algorithmic bytes/ray (32 + 16 + 24*N_box +
+            36*N_tri, N_* from the oracle's duplicate-free traversal of the same BVH) x rays / CUDA-event
+            time of its launches (a separate pass with per-kernel-class events on the library's stream).
+            bound = "l2" when the traversal working set (nodes + triangle records) is L2 resident (C1-C4):
+            peak = the L2 read bandwidth measured in this run at that working-set size; bound = "hbm" (C5):
+            peak = MEASURED_PEAKS.json hbm_gbs.
   cpu_baseline  the CPU restatement of the reference (oracle, faithful traversal, reference task
-            scheduling, all host threads) on a bounded pixel window of the same workload.
-
-N > 1 (torchrun): every rank holds a scene replica and renders its own block of sample indices
-(weak scaling: per-GPU work fixed); one NCCL reduce of the accumulators per step.
+            scheduling, all host threads) on a bounded sample of the same frame — every k-th 4x4 tile over
+            the WHOLE frame at a few spp — plus `ideal_value`: the same with the reference's duplicate-left
+            push (raytracer.odin:395-409) removed.
 """
 import argparse
 import json
@@ -36,6 +43,7 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 SEED = 20261018
+L2_RESIDENT_BYTES = 100 << 20  # traversal working sets below this are served from the 126 MB L2
 
 
 def build_scene(config, finish_with, scale=None):
@@ -105,44 +113,35 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md, no MEASURED_PEAKS.json)"
 
 
-def cpu_leg(scene, cfg, target_s, ideal_counts=True):
-    """Time the CPU restatement on a centred pixel window sized for ~target_s seconds of wall time;
-    also count the duplicate-free traversal's box / triangle tests per ray (algorithmic need)."""
+def cpu_leg(scene, cfg, target_s):
+    """The CPU restatement on a bounded sample of the frame: every `stride`-th 4x4 tile in x and y over the
+    WHOLE frame, `spp` samples, sized for ~target_s seconds of wall time.  Returns run(mode) -> (Mrays/s,
+    counters, seconds), the thread count and a description of the sample."""
     from oracle import binding as orc
 
     w, h, depth = cfg["width"], cfg["height"], cfg["ray_depth"]
     nat = orc.OracleScene(scene, native=True)
     threads = max(1, nat.lib.orc_hardware_threads())
-
-    def window(nx, ny):
-        return (w // 2 - nx // 2, h // 2 - ny // 2, w // 2 - nx // 2 + nx, h // 2 - ny // 2 + ny)
-
-    # pilot: 64x36 window, 1 spp
-    t0 = time.perf_counter()
-    _, c = nat.render(w, h, depth, 1, seed=SEED, mode=0, schedule=0, threads=threads, window=window(64, 36))
-    pilot_s = max(time.perf_counter() - t0, 1e-4)
-    rate = c["rays"] / pilot_s
-    rays_per_px = c["rays"] / (64 * 36)
-    want_px = max(64 * 36, rate * target_s / max(rays_per_px, 1e-9))
     spp = 4
-    nx = int(min(w, max(64, (want_px / spp * 16 / 9) ** 0.5))) // 4 * 4
-    ny = int(min(h, max(36, nx * 9 // 16))) // 4 * 4
-    win = window(nx, ny)
+    # pilot: every 32nd tile (~1/1024 of the frame), 1 spp
+    t0 = time.perf_counter()
+    _, c = nat.render(w, h, depth, 1, seed=SEED, mode=0, schedule=0, threads=threads, tile_stride=32)
+    pilot_s = max(time.perf_counter() - t0, 1e-4)
+    n_tiles = ((w + 3) // 4) * ((h + 3) // 4)
+    rays_per_tile_spp = c["rays"] / max(n_tiles / 1024.0, 1.0)
+    rate = c["rays"] / pilot_s
+    want_tiles = rate * target_s / max(rays_per_tile_spp * spp, 1e-9)
+    stride = int(max(1, min(32, round((n_tiles / max(want_tiles, 1.0)) ** 0.5))))
 
-    def run():
+    def run(mode=0):
         t0 = time.perf_counter()
-        _, c = nat.render(w, h, depth, spp, seed=SEED, mode=0, schedule=0, threads=threads, window=win)
+        _, c = nat.render(w, h, depth, spp, seed=SEED, mode=mode, schedule=0, threads=threads, tile_stride=stride)
         dt = time.perf_counter() - t0
         return c["rays"] / dt / 1e6, c, dt
 
-    sample = f"{nx}x{ny} centre window of the {w}x{h} frame, {spp} spp, depth {depth}"
-    counts = None
-    if ideal_counts:
-        chk = orc.OracleScene(scene, native=True)
-        _, ci = chk.render(w, h, depth, 1, seed=SEED, mode=1, schedule=0, threads=threads, window=window(256, 144))
-        counts = {"n_box": ci["box_tests"] / ci["rays"], "n_tri": ci["tri_tests"] / ci["rays"],
-                  "node_pops": ci["node_pops"] / ci["rays"], "rays": ci["rays"]}
-    return run, threads, sample, counts
+    sample = (f"rate on a sample: every {stride}th 4x4-pixel tile in x and y over the whole {w}x{h} frame "
+              f"(1/{stride * stride} of the pixels), {spp} spp, depth {depth}")
+    return run, threads, sample, nat
 
 
 def reference_arm(args):
@@ -153,8 +152,8 @@ def reference_arm(args):
         return
     from oracle import binding as orc
 
-    scene, cfg = build_scene(args.config, orc.bvh_build)
-    run, threads, sample, _ = cpu_leg(scene, cfg, target_s=8.0, ideal_counts=False)
+    scene, cfg = build_scene(args.config, orc.bvh_build)  # the oracle's own bvh_build: nothing of the library on this arm
+    run, threads, sample, _ = cpu_leg(scene, cfg, target_s=6.0)
     for _ in range(args.warmup):
         run()
     vals, t0 = [], time.perf_counter()
@@ -163,14 +162,18 @@ def reference_arm(args):
     total = time.perf_counter() - t0
     rays = sum(v[1]["rays"] for v in vals)
     value = rays / sum(v[2] for v in vals) / 1e6
+    ideal_v, _, _ = run(mode=1)
+    spp = args.spp or cfg["spp"] or 64
     line = {
         "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.config, cfg, scene, None),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.config, cfg, scene, spp),
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": sample,
+                         "ideal_value": ideal_v,
                          "note": "CPU restatement of the reference render loop (faithful traversal order incl. the "
-                                 "duplicate-left push, reference 4x4x32 task scheduling); Odin toolchain unavailable"},
+                                 "duplicate-left push, reference 4x4x32 task scheduling); Odin toolchain unavailable. "
+                                 "ideal_value: the same loop with the duplicate push removed (BASELINE.md §3)"},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -180,11 +183,11 @@ def reference_arm(args):
 def workload_config(name, cfg, scene, spp):
     return {"workload": f"BASELINE config {name}: generated {len(scene.triangles)}-triangle glTF "
                         f"({cfg['gen']}), {cfg['width']}x{cfg['height']}, ray-depth {cfg['ray_depth']}, "
-                        f"{spp if spp else cfg['spp']} spp per step",
+                        f"{spp} spp per frame (one step = one frame, sample-split over the GPUs)",
             "triangles": int(len(scene.triangles)), "light_triangles": int(len(scene.light_triangles)),
             "width": cfg["width"], "height": cfg["height"], "ray_depth": cfg["ray_depth"],
-            "spp_per_step": spp if spp else cfg["spp"],
-            "l2": "per-step path state (>1 GB) and queues exceed the 126 MB L2; no explicit flush"}
+            "spp_per_step": spp,
+            "l2": "per-step path state (>1 GB per wave) and queues exceed the 126 MB L2; no explicit flush"}
 
 
 def main():
@@ -193,8 +196,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--config", default="C2")
-    ap.add_argument("--spp", type=int, default=0, help="samples per step (default: the config's spp)")
+    ap.add_argument("--config", default="C4")
+    ap.add_argument("--spp", type=int, default=0, help="samples per frame (default: the config's spp; C5: 64)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--bvh", choices=("host", "device"), default="host",
                     help="builder used by finish_scene before the timed region (identical output)")
@@ -247,9 +250,12 @@ def main():
     accum = torch.zeros(8, npix, device="cuda", dtype=torch.float32)
 
     def step(i):
-        # weak scaling: every rank renders `spp` samples of its own block of the global sample axis
-        first, cnt = multigpu.sample_partition(i * spp * world, spp * world, rank, world)
-        r.render_device(w, h, depth, first, cnt, accum.data_ptr())
+        # one frame: the frame's spp samples are divided over the ranks (strong scaling); trials replay
+        # disjoint sample ranges (frame i renders samples [i*spp, (i+1)*spp))
+        first, cnt = multigpu.sample_partition(i * spp, spp, rank, world)
+        accum.zero_()
+        if cnt > 0:
+            r.render_device(w, h, depth, first, cnt, accum.data_ptr())
         if world > 1:
             multigpu.reduce_accum(accum, 0)  # the one collective of the path: one NCCL reduce per frame
 
@@ -266,7 +272,7 @@ def main():
         e0.record(stream)
         for i in range(args.steps):
             step(args.warmup + i)
-            marks[i].record(stream)  # per-step times: best / median / worst like the reference's summary
+            marks[i].record(stream)  # per-frame times: best / median / worst like the reference's summary
         e1.record(stream)
         torch.cuda.synchronize()
     step_ms = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
@@ -283,33 +289,49 @@ def main():
         ms = float(tmax[0])
     rays, traced, paths, launches, light_rays = (float(x) for x in t[1:])
     value = rays / (ms * 1e-3) / 1e6
+    # the frame on rank 0 holds every rank's samples: count plane == spp everywhere
+    if rank == 0:
+        cnt_plane = accum[6] + accum[7] * float(1 << 20)
+        assert float(cnt_plane.min()) == float(cnt_plane.max()) == float(spp), "reduced frame does not hold spp samples per pixel"
 
-    # ---- e2e: public host call, HOST buffers, scene H2D + Sample_Stats D2H inside the timed region
-    r.set_stream(None)
-    cs, keep = scene.to_c()
+    # ---- e2e: public host calls, HOST buffers; per frame: scene H2D + render + reduce + ONE Sample_Stats image D2H
     h2d = (scene.triangles.nbytes + scene.bvh.nbytes + scene.light_triangles.nbytes + scene.light_bvh.nbytes +
            scene.materials.nbytes + sum(t_.nbytes for t_ in scene.textures) +
            (scene.env_map.nbytes if scene.env_map is not None else 0))
     out = np.zeros(npix, dtype=api.cabi.STATS_DTYPE)
     e2e_steps = max(2, min(args.steps, 3))
-
     e2e_parts = []
+    if world == 1:
+        r.set_stream(None)
 
     def e2e_step(i):
-        first, cnt = multigpu.sample_partition(i * spp * world, spp * world, rank, world)
+        first, cnt = multigpu.sample_partition(i * spp, spp, rank, world)
         ta = time.perf_counter()
         r.upload_scene(scene)
         tb = time.perf_counter()
-        r.render(w, h, depth, cnt, first, out)
+        if world == 1:
+            r.render(w, h, depth, cnt, first, out)
+        else:
+            accum.zero_()
+            if cnt > 0:
+                r.render_device(w, h, depth, first, cnt, accum.data_ptr())
+            multigpu.reduce_accum(accum, 0)
+            if rank == 0:
+                r.unpack_accum(w, h, accum.data_ptr(), out)  # the frame's ONE host image (synchronises)
+            else:
+                torch.cuda.synchronize()
         e2e_parts.append(((tb - ta) * 1e3, (time.perf_counter() - tb) * 1e3))
 
-    e2e_step(0)
+    e2e_step(args.warmup + args.steps)
+    out[:] = 0
     r.reset_stats()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
-        e2e_step(1 + i)
+        e2e_step(args.warmup + args.steps + 1 + i)
+    if world > 1:
+        dist.barrier()
     e2e_s = time.perf_counter() - t0
     e2e_rays = float(r.stats()["rays_closest"])
     te = torch.tensor([e2e_s, e2e_rays], device="cuda", dtype=torch.float64)
@@ -319,34 +341,43 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.SUM)
         e2e_s = float(tm[0])
     e2e_value = float(te[1]) / e2e_s / 1e6
+    if rank == 0:
+        assert int(out["count"].min()) == int(out["count"].max()) == spp * e2e_steps, "e2e image is not ONE full frame per step"
 
-    # ---- roofline of the dominant kernel (rank 0): one extra step with per-kernel-class CUDA events
+    # ---- roofline of the dominant kernel (rank 0): a separate pass with per-kernel-class CUDA events
     roof, cpu = None, None
     if rank == 0:
         r.set_stream(stream.cuda_stream)
         r.reset_stats()
         r.set_profiling(True)
-        r.render_device(w, h, depth, 10_000_000, spp, accum.data_ptr())
+        wave_paths = int(os.environ.get("ORT_WAVE_PATHS", 1 << 25))  # library default: 2^25 paths per wave
+        spp_per_wave = max(1, wave_paths // npix)
+        prof_spp = min(spp, 16 * spp_per_wave)  # 16 waves: per-launch times do not depend on the frame's length
+        accum.zero_()
+        r.render_device(w, h, depth, 10_000_000, prof_spp, accum.data_ptr())
         torch.cuda.synchronize()
         ps = r.stats()
         r.set_profiling(False)
-        peak, peak_src = measured_peak()
+        hbm_peak, hbm_src = measured_peak()
         counts = None
         if not args.no_cpu:
-            run, threads, sample, counts = cpu_leg(scene, cfg, target_s=12.0)
-            v, c, dt = run()
+            run, threads, sample, nat = cpu_leg(scene, cfg, target_s=10.0)
+            v, c, dt = run(0)
+            vi, ci, dti = run(1)
             cpu = {"value": v, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": sample,
                    "seconds": dt, "rays": c["rays"],
+                   "ideal_value": vi, "ideal_seconds": dti,
                    "reference_node_pops_per_ray": c["node_pops"] / c["rays"],
-                   "reference_tri_tests_per_ray": c["tri_tests"] / c["rays"]}
-        if counts:
-            bpr = 32 + 16 + 24 * counts["n_box"] + 36 * counts["n_tri"]
-        else:
-            bpr = None
+                   "reference_tri_tests_per_ray": c["tri_tests"] / c["rays"],
+                   "ideal_node_pops_per_ray": ci["node_pops"] / ci["rays"],
+                   "ideal_tri_tests_per_ray": ci["tri_tests"] / ci["rays"],
+                   "gpu_over_cpu": {"faithful": value / v, "ideal": value / vi, "n_gpus": world, "cores": threads},
+                   "note": "value: the reference as written (duplicate-left push, raytracer.odin:395-409); "
+                           "ideal_value: the same loop without the duplicate push"}
+            counts = {"n_box": ci["box_tests"] / ci["rays"], "n_tri": ci["tri_tests"] / ci["rays"]}
+        bpr = (32 + 16 + 24 * counts["n_box"] + 36 * counts["n_tri"]) if counts else None
         trace_s = ps["trace_ms"] * 1e-3
-        wave_paths = int(os.environ.get("ORT_WAVE_PATHS", 1 << 25))  # library default: 2^25 paths per wave
-        spp_per_wave = max(1, wave_paths // npix)
-        n_launch = depth * ((spp + spp_per_wave - 1) // spp_per_wave)  # one k_trace<closest> per bounce per wave
+        n_launch = depth * ((prof_spp + spp_per_wave - 1) // spp_per_wave)  # one k_trace<closest> per bounce per wave
         traffic = None
         tpath = os.path.join(ROOT, "profiles", f"ncu_traffic_{args.config.lower()}.json")
         if os.path.exists(tpath):  # dram__bytes_read+write per launch from the committed ncu --set full capture
@@ -354,55 +385,65 @@ def main():
                 tj = json.load(f)
             if tj.get("spp_per_wave") == spp_per_wave:
                 traffic = tj["k_trace_closest"]["dram_bytes_per_launch_avg"]
-        roof = {"bound": "hbm", "kernel": "k_trace", "unit": "GB/s", "peak": peak, "peak_source": peak_src,
+        achieved = (bpr * ps["rays_traced"] / trace_s / 1e9) if bpr else None
+        # the traversal working set (nodes + triangle records) of C1-C4 is L2 resident, so the roof
+        # is the box's L2 read bandwidth, measured here with the library's streaming-read probe on a working set
+        # of the scene's size (at least 32 MB to stay out of L1); C5 (2.3 GB) streams from HBM
+        ws = ps["wide_nodes"] * 128 + ps["light_wide_nodes"] * 128 + (len(scene.triangles) + len(scene.light_triangles)) * 64
+        l2_bound = ws < L2_RESIDENT_BYTES
+        probe = max(ws, 32 << 20) if l2_bound else min(max(ws, 1 << 30), 4 << 30)
+        read_gbs = r.bench_read_bw(probe, 20 if probe <= (256 << 20) else 5)
+        if l2_bound:
+            peak, peak_src = read_gbs, ("measured in this run: ort_bench_read_bw (256-bit read-only loads from all SMs) over "
+                                        f"a {probe >> 20} MB working set = L2 read bandwidth")
+        else:
+            peak, peak_src = hbm_peak, hbm_src
+        roof = {"bound": "l2" if l2_bound else "hbm", "kernel": "k_trace<closest>", "unit": "GB/s",
+                "achieved": achieved, "peak": peak, "frac": (achieved / peak) if achieved else None,
+                "peak_source": peak_src, "traffic": traffic,
+                "working_set_bytes": int(ws), "hbm_peak": hbm_peak, "hbm_read_probe_gbs": None if l2_bound else read_gbs,
                 "bytes_per_ray": bpr, "n_box": counts["n_box"] if counts else None,
                 "n_tri": counts["n_tri"] if counts else None,
-                "rays_per_step": ps["rays_traced"], "launches_per_step": n_launch,
-                "kernel_ms_per_step": ps["trace_ms"], "avg_launch_ms": ps["trace_ms"] / n_launch,
-                "achieved": (bpr * ps["rays_traced"] / trace_s / 1e9) if bpr else None,
-                "traffic": traffic,
+                "profiled_pass": f"{prof_spp} spp ({n_launch // depth} waves of {spp_per_wave} spp), kernel classes serialised",
+                "rays_per_pass": ps["rays_traced"], "launches_per_pass": n_launch,
+                "kernel_ms_per_pass": ps["trace_ms"], "avg_launch_ms": ps["trace_ms"] / n_launch,
                 "algorithmic_bytes_per_launch": (bpr * ps["rays_traced"] / n_launch) if bpr else None,
                 "trace_grays_per_s": ps["rays_traced"] / trace_s / 1e9,
-                "step_breakdown_ms": {"trace": ps["trace_ms"], "light": ps["light_ms"], "shade": ps["shade_ms"],
+                "pass_breakdown_ms": {"trace": ps["trace_ms"], "light": ps["light_ms"], "shade": ps["shade_ms"],
                                       "other": ps["other_ms"]},
-                "note": "C1-C4 traversal working sets sit in the 126 MB L2 (SURVEY §8d), so achieved "
-                        "algorithmic GB/s may exceed the HBM copy peak; ncu dram bytes are in profiles/"}
-        roof["frac"] = (roof["achieved"] / peak) if roof["achieved"] else None
-        # second fraction: compulsory HBM traffic of the wavefront design per traced ray and bounce —
-        # k_trace reads the ray (32 B) and writes the hit (16 B); k_shade reads ray, hit, pending payload and
-        # light sum (84 B) and writes the next ray + payload + light-queue entry (68 B) — against the HBM peak
+                "note": "the limiting resource of the traversal is issue slots x SIMD efficiency (ncu: 13-15 of 32 lanes "
+                        "per instruction on bounce rays), not bytes: frac says how far the kernel sits from a design that "
+                        "streams the algorithmic bytes at the roof; `traffic` (ncu dram bytes per launch) far below "
+                        "algorithmic_bytes_per_launch means the bytes come from L2/L1"}
+        # compulsory HBM traffic of the wavefront design per traced ray and bounce — k_trace reads the ray (32 B) and
+        # writes the hit (16 B); k_shade reads ray, hit, pending payload and light sum (84 B) and writes the next ray +
+        # payload + light-queue entry (68 B) — against the HBM peak
         state_bpr = 32 + 16 + 84 + 68
         roof["state_traffic"] = {"bytes_per_ray_bounce": state_bpr, "unit": "GB/s",
                                  "achieved": state_bpr * traced / world / (ms * 1e-3) / 1e9,  # per GPU
-                                 "frac": state_bpr * traced / world / (ms * 1e-3) / 1e9 / peak}
-        # C1-C4 traversal working sets are L2 resident, so the same algorithmic GB/s is also
-        # held against the box's L2 read bandwidth, measured here with the library's streaming-read probe
-        # on a working set of the scene's size (nodes + traversal triangles, at least 32 MB to stay out of L1)
-        ws = ps["wide_nodes"] * 128 + ps["light_wide_nodes"] * 128 + (len(scene.triangles) + len(scene.light_triangles)) * 64
-        probe = max(ws, 32 << 20)
-        l2_gbs = r.bench_read_bw(probe, 20 if probe <= (256 << 20) else 5)
-        roof["l2"] = {"working_set_bytes": int(ws), "probe_bytes": int(probe), "peak": l2_gbs, "unit": "GB/s",
-                      "peak_source": "measured in this run: ort_bench_read_bw, 256-bit read-only loads from all SMs",
-                      "frac": (roof["achieved"] / l2_gbs) if roof["achieved"] else None}
+                                 "frac": state_bpr * traced / world / (ms * 1e-3) / 1e9 / hbm_peak}
 
     if rank == 0:
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args.config, cfg, scene, spp),
             "samples_per_s": paths / (ms * 1e-3), "frames_1080p_spp_per_s": paths / (ms * 1e-3) / 2073600.0,
             "rays_traced_per_s": traced / (ms * 1e-3), "light_pdf_rays_per_s": light_rays / (ms * 1e-3),
             "step_ms": {"best": min(step_ms), "median": float(np.median(step_ms)), "worst": max(step_ms)},
-            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d),
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d) * world,
                     "d2h_bytes_per_step": int(npix * 52), "steps": e2e_steps,
                     "upload_ms": [round(a, 2) for a, _ in e2e_parts[1:]],
                     "render_ms": [round(b, 2) for _, b in e2e_parts[1:]],
-                    "what": "ort_upload_scene (host scene -> HBM, wide-BVH re-emission) + ort_render into host "
-                            "Sample_Stats, wall clock"},
+                    "what": ("ort_upload_scene (host scene -> HBM, wide-BVH re-emission) + ort_render into host Sample_Stats"
+                             if world == 1 else
+                             "per rank ort_upload_scene + ort_render_device of its sample block, ONE NCCL reduce, "
+                             "ort_unpack_accum into ONE host Sample_Stats image on rank 0") + "; wall clock, max over ranks"},
             "gpu_launches": int(launches), "clocks": clocks.summary(),
             "roofline": roof, "cpu_baseline": cpu,
-            "wide_bvh": {"nodes": st["wide_nodes"], "depth": st["wide_depth"], "device_bytes": st["device_bytes"]},
+            "wide_bvh": {"nodes": st["wide_nodes"], "depth": st["wide_depth"], "device_bytes": st["device_bytes"],
+                         "max_stack": st["wide_max_stack"], "reference_stack_need": st["reference_stack_need"]},
         }
         print(json.dumps(line), flush=True)
     r.close()

@@ -53,6 +53,8 @@ def load(native=False):
         "orc_primary_hits": (None, [vp, u32, u32, u64, u64, i32, vp, vp, C.POINTER(Counters), i32, vp]),
         "orc_render": (None, [vp, u32, u32, C.c_int32, u64, u64, u64, i32, i32, i32, u32, u32, u32, u32, vp,
                               C.POINTER(Counters)]),
+        "orc_render_strided": (None, [vp, u32, u32, C.c_int32, u64, u64, u64, i32, i32, i32, u32, u32, u32, u32, u32, vp,
+                                      C.POINTER(Counters)]),
         "orc_shade": (None, [pf, pf, f, f, pf, pf, pf]),
         "orc_cosine_weighted_pdf": (f, [pf, pf]),
         "orc_vndf_sampling_pdf": (f, [pf, pf, f, pf]),
@@ -131,16 +133,17 @@ class OracleScene:
         return out, rays, c.as_dict()
 
     def render(self, w, h, ray_depth, n_samples, first_sample=0, seed=0, mode=0, schedule=1, threads=8,
-               window=None, out=None):
-        """Returns (Sample_Stats array [h*w], counters)."""
+               window=None, out=None, tile_stride=1):
+        """Returns (Sample_Stats array [h*w], counters).  tile_stride > 1: only every tile_stride-th 4x4 tile
+        in x and y (a bounded sample spread over the whole frame)."""
         from raytracer_odin_b200 import cabi
 
         if out is None:
             out = np.zeros(w * h, cabi.STATS_DTYPE)
         x0, y0, x1, y1 = window if window else (0, 0, w, h)
         c = Counters()
-        self.lib.orc_render(self.ref, w, h, ray_depth, first_sample, n_samples, seed, mode, schedule, threads,
-                            x0, y0, x1, y1, out.ctypes.data, C.byref(c))
+        self.lib.orc_render_strided(self.ref, w, h, ray_depth, first_sample, n_samples, seed, mode, schedule, threads,
+                                    x0, y0, x1, y1, tile_stride, out.ctypes.data, C.byref(c))
         return out, c.as_dict()
 
 

@@ -817,8 +817,11 @@ void orc_trace_rays(const ort_scene* scene, const ort_ray* rays, int64_t n, int 
         for (int64_t i = tid; i < n; i += threads) {
             Ray r = {v3(rays[i].o), v3(rays[i].d)};
             c.last_tie_t = std::numeric_limits<float>::quiet_NaN();
+            const uint64_t drops_before = c.stack_drops;
             Hit h = cast_ray(sv, r, INF_F32, &c);
-            if (ties_out) ties_out[i] = (h.trig >= 0 && c.last_tie_t + RAY_EPS == h.t) ? 1 : 0;
+            // bit 0: exact-t tie; bit 1: the 64-entry stack (raytracer.odin:379) dropped a push on this ray
+            if (ties_out) ties_out[i] = (uint8_t)(((h.trig >= 0 && c.last_tie_t + RAY_EPS == h.t) ? 1 : 0) |
+                                                  (c.stack_drops > drops_before ? 2 : 0));
             out[i].t = h.t; out[i].u = h.u; out[i].v = h.v;
             out[i].tri = (int32_t)h.trig;
             out[i].material = h.trig < 0 ? -1 : (int32_t)scene->triangles[h.trig].material_index;
@@ -883,9 +886,13 @@ void orc_primary_hits(const ort_scene* scene, uint32_t w, uint32_t h, uint64_t s
 //               per-pixel summation order is sample order regardless of thread count (use for
 //               CHECKING).
 // Pixel box [x0,x1) x [y0,y1) restricts rendering to a window (bounded CPU samples).
-void orc_render(const ort_scene* scene, uint32_t w, uint32_t h, int32_t ray_depth, uint64_t first_sample,
-                uint64_t n_samples, uint64_t seed, int mode, int schedule, int threads, uint32_t x0,
-                uint32_t y0, uint32_t x1, uint32_t y1, ort_sample_stats* out, orc_counters* counters) {
+// tile_stride > 1 renders only the 4x4-pixel tiles whose tile coordinates are both multiples of it: a
+// bounded sample SPREAD OVER THE WHOLE FRAME (sky, horizon and ground in the frame's own proportions)
+// instead of a centre window, for timing the CPU arm on workloads too large to render in full.
+void orc_render_strided(const ort_scene* scene, uint32_t w, uint32_t h, int32_t ray_depth, uint64_t first_sample,
+                        uint64_t n_samples, uint64_t seed, int mode, int schedule, int threads, uint32_t x0,
+                        uint32_t y0, uint32_t x1, uint32_t y1, uint32_t tile_stride, ort_sample_stats* out,
+                        orc_counters* counters) {
     SceneView sv{scene, mode};
     M4 M = pixel_to_ray_dir(scene->cam, w, h);
     if (threads < 1) threads = 1;
@@ -904,6 +911,7 @@ void orc_render(const ort_scene* scene, uint32_t w, uint32_t h, int32_t ray_dept
         uint32_t start_x = (uint32_t)(TILE * x_coord), end_x = std::min<uint32_t>(start_x + TILE, w);
         uint32_t start_y = (uint32_t)(TILE * y_coord), end_y = std::min<uint32_t>(start_y + TILE, h);
         if (start_x >= x1 || end_x <= x0 || start_y >= y1 || end_y <= y0) return;
+        if (tile_stride > 1 && (x_coord % tile_stride != 0 || y_coord % tile_stride != 0)) return;
         for (uint64_t sample = 0; sample < num_samples; sample++)
             for (uint32_t px = start_x; px < end_x; px++)
                 for (uint32_t py = start_y; py < end_y; py++) {
@@ -934,6 +942,13 @@ void orc_render(const ort_scene* scene, uint32_t w, uint32_t h, int32_t ray_dept
     work(0);
     for (auto& t : pool) t.join();
     if (counters) for (auto& c : cs) add_counters(counters, c);
+}
+
+void orc_render(const ort_scene* scene, uint32_t w, uint32_t h, int32_t ray_depth, uint64_t first_sample,
+                uint64_t n_samples, uint64_t seed, int mode, int schedule, int threads, uint32_t x0,
+                uint32_t y0, uint32_t x1, uint32_t y1, ort_sample_stats* out, orc_counters* counters) {
+    orc_render_strided(scene, w, h, ray_depth, first_sample, n_samples, seed, mode, schedule, threads, x0, y0, x1, y1, 1,
+                       out, counters);
 }
 
 // --- shading / texture KAT entry points -----------------------------------------------------
