@@ -65,6 +65,17 @@ def main():
     rays["d"] = (dd / np.linalg.norm(dd, axis=1, keepdims=True)).astype(np.float32)
     hits, _ = orc.OracleScene(sc).trace_rays(rays, mode=0)
     np.savez_compressed(os.path.join(HERE, "soup_trace.npz"), rays=rays, hits=hits)
+    # (4) BASELINE config C1 as quoted: Cornell box, 256x256, ray-depth 6, 64 spp (schedule 1: per-pixel sums in
+    #     sample order whatever the thread count)
+    with tempfile.TemporaryDirectory() as d:
+        s = gltf.read_gltf(scenegen.cornell(os.path.join(d, "c1.gltf")))
+    w = h = 256
+    s.fov_x = s.apply_render_config(w, h)
+    s.finish(orc.bvh_build)
+    px, c = orc.OracleScene(s).render(w, h, 6, 64, seed=SEED, mode=0, schedule=1, threads=8)
+    assert np.all(px["count"] == 64)
+    np.savez_compressed(os.path.join(HERE, "cornell_c1_256.npz"), total=px["total"], seed=np.array(SEED),
+                        n_rays=np.array([c["rays"]]))
     print("golden fixtures written to", HERE)
 
 

@@ -1,7 +1,8 @@
 """N > 1 path on CPU: world_size-2 gloo.  Each rank renders its block of the sample axis (with the
 CPU oracle standing in for the GPU replica — this is a test), packs the planar accumulator the
-library uses (total | total_squared | count), and ONE reduce to rank 0 must reproduce the
-single-process render of the whole sample range up to f32 summation order."""
+library uses (total | total_squared | count_lo | count_hi), and ONE reduce to rank 0 must reproduce the
+single-process render of the whole sample range up to f32 summation order — the strong-scaling split
+bench.py uses: one fixed frame, its sample range divided over the ranks."""
 import os
 
 import numpy as np
@@ -14,7 +15,8 @@ def _planar(px, npix):
     acc = np.zeros((8, npix), np.float32)
     acc[0:3] = px["total"].T
     acc[3:6] = px["total_squared"].T
-    acc[6] = px["count"]
+    acc[6] = px["count"] & 0xFFFFF  # count = lo + 2^20 * hi: both planes exact in f32, also under the sum-reduce
+    acc[7] = px["count"] >> 20
     return acc
 
 
@@ -52,5 +54,5 @@ def test_sample_split_reduce_world2(scene_dir, tmp_path):
     s.finish(orc.bvh_build)
     px, _ = orc.OracleScene(s).render(w, h, depth, spp, seed=seed, threads=2)
     want = _planar(px, w * h)
-    assert np.array_equal(got[6], want[6]) and np.all(got[6] == spp)
+    assert np.array_equal(got[6] + got[7] * (1 << 20), want[6] + want[7] * (1 << 20)) and np.all(got[6] == spp)
     np.testing.assert_allclose(got[:6], want[:6], rtol=1e-5, atol=1e-6)

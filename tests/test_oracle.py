@@ -353,3 +353,20 @@ def test_pixel_to_ray_dir_and_tonemap(scenes):
     a = orc.get_rgb_image(px, 4, 4)
     b = output.get_rgb_image(px, 4, 4)
     assert np.abs(a.astype(int) - b.astype(int)).max() <= 1
+
+
+def test_strided_tile_sample_is_a_subset_of_the_frame(scenes):
+    """orc_render_strided (bench.py's bounded CPU sample): every stride-th 4x4 tile in x and y, spread over the
+    whole frame; the rendered pixels equal the full render's, all others stay untouched."""
+    s = scenes("cornell", 40, 24)
+    o = orc.OracleScene(s)
+    full, cf = o.render(40, 24, 3, 2, seed=3, schedule=1, threads=2)
+    part, cp = o.render(40, 24, 3, 2, seed=3, schedule=1, threads=2, tile_stride=2)
+    full, part = full.reshape(24, 40), part.reshape(24, 40)
+    yy, xx = np.mgrid[0:24, 0:40]
+    sel = ((xx // 4) % 2 == 0) & ((yy // 4) % 2 == 0)
+    sel = sel[::-1]  # Sample_Stats rows are flipped (main.odin:95)
+    assert sel.sum() == 5 * 3 * 16
+    assert np.array_equal(part[sel], full[sel])
+    assert np.all(part["count"][~sel] == 0)
+    assert 0 < cp["rays"] < cf["rays"]
