@@ -157,6 +157,7 @@ __device__ __forceinline__ bool tri_uv(const RaySetup& r, float4 a, float4 b, fl
 
 } // namespace ort
 #include "traverse.cuh"
+#include "traverse_pool.cuh"
 namespace ort {
 
 // ------------------------------------------------------------------------------------------------

@@ -197,10 +197,24 @@ int main(int argc, char** argv) {
         int previews = 0;
         t0 = now_s();
         double next_preview = t0 + a.preview_every;
+        // progress every 10 s: samples ENQUEUED (the device lags by at most a few waves per GPU, the host is
+        // throttled by the interrupt flag), i.e. the sustained rate of the whole loop incl. previews
+        double last_report = t0;
+        uint64_t last_rendered = 0;
+        std::vector<double> interval_rates;
         while (!g_interrupt) {
             rendered += frame_render(first, chunk);
             first += chunk; // an interrupted call still consumes its index range: no sample index is ever reused
             const double now = now_s();
+            if (now - last_report >= 10.0) {
+                const double rate = (double)(rendered - last_rendered) * (double)w * (double)h / (now - last_report) / 1e6;
+                std::printf("t=%.1fs  %llu samples per pixel  %.1f Msamples/s over the last %.1fs\n", now - t0,
+                            (unsigned long long)rendered, rate, now - last_report);
+                std::fflush(stdout);
+                interval_rates.push_back(rate);
+                last_report = now;
+                last_rendered = rendered;
+            }
             if (a.duration > 0 && now - t0 >= a.duration) g_interrupt = 1;
             if (!a.preview.empty() && now >= next_preview && !g_interrupt) {
                 // get_rgb_image on the device (output.odin:30-80): snapshot now, enqueue the next chunk, THEN wait
@@ -231,6 +245,13 @@ int main(int argc, char** argv) {
         std::printf("Rendered %llu samples in %.2fs\n", (unsigned long long)rendered, dt);
         std::printf("%.1f Mrays/s sustained, %.1f Msamples/s, %d previews (host blocked %.1f ms in total)\n",
                     (double)st.rays_closest / dt / 1e6, (double)st.paths / dt / 1e6, previews, host_blocked * 1e3);
+        if (interval_rates.size() > 1) { // steady state: the 10-s intervals after the first
+            std::vector<double> ss(interval_rates.begin() + 1, interval_rates.end());
+            std::sort(ss.begin(), ss.end());
+            const double med = ss[ss.size() / 2], rays_per_sample = st.paths ? (double)st.rays_closest / (double)st.paths : 0.0;
+            std::printf("steady state after 10 s: median %.1f Msamples/s = %.1f Mrays/s (min %.1f, max %.1f Msamples/s over %zu intervals)\n",
+                        med, med * rays_per_sample, ss.front(), ss.back(), ss.size());
+        }
     } else {
         const long trials = a.times > 0 ? a.times : 1;
         std::vector<double> timings;

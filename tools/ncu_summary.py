@@ -54,7 +54,8 @@ def full(rep, traffic=None, cfg=None, spp_per_wave=None):
     for r in data:
         name = r[ix["Kernel Name"]][:26]
         print(name + " | " + " | ".join(r[ix[m]] for m, _ in COLS if m in ix))
-        if "k_trace<1, 0, 0>" in r[ix["Kernel Name"]] or "k_trace<(bool)1, (bool)0, (bool)0>" in r[ix["Kernel Name"]]:
+        kn = r[ix["Kernel Name"]]
+        if any(s in kn for s in ("k_trace<0>", "k_trace<(bool)0>", "k_trace<false>", "k_trace<1, 0, 0>", "k_trace<(bool)1, (bool)0, (bool)0>")):
             def to_bytes(m):
                 return float(r[ix[m]].replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[ix[m]]]
             ms = float(r[ix["gpu__time_duration.sum"]]) * {"ns": 1e-6, "us": 1e-3, "ms": 1.0}[units[ix["gpu__time_duration.sum"]]]
