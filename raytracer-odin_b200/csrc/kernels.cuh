@@ -91,18 +91,28 @@ struct RaySetup {
 // distances carry an absolute error of a few ulp of (|o| + |box|) / |d|.  Each slab distance is
 // widened by `pad` = 16 ulp of that magnitude so every box the reference enters is entered here
 // too; a superset of boxes cannot change the closest hit, only the triangle test decides.
+//
+// Direction components that are zero or tiny.  The reference divides by d: with d.x == 0 its slab interval is
+// (-inf, +inf) when the origin lies inside the slab and empty otherwise.  The form used here, plane * (1/d) +
+// (-o/d -+ pad), turns that into inf - inf = NaN, and fmaxf / fminf DROP NaN operands: the x slab would never
+// reject, and the ray would visit every box of its yz column — one such ray was measured at 1.2-2.0 ms of serial
+// traversal on the 1 M-triangle scene (profiles/r2_zero_direction_components.md), and an axis-aligned camera
+// produces a few per wave (exact cancellation in pixel_to_ray_dir on one pixel column and one row).  For the box
+// tests |d| is therefore clamped to 1e-18: every product stays finite for coordinates up to 1e20, an origin inside
+// the slab (within the pad) still gets an interval that covers every distance the other axes allow, and an origin
+// outside gets an interval beyond them — the same decisions as the reference's, as a superset.  The triangle solve
+// keeps the ray's own direction.
 __device__ __forceinline__ RaySetup make_ray(float4 o4, float4 d4, const float* pad_scale) {
     RaySetup r;
     r.dx = d4.x; r.dy = d4.y; r.dz = d4.z;
     r.ox = addr(o4.x, mulr(d4.x, RAY_EPS));
     r.oy = addr(o4.y, mulr(d4.y, RAY_EPS));
     r.oz = addr(o4.z, mulr(d4.z, RAY_EPS));
-#ifdef ORT_FAST_RCP
-    // the slab distances are padded by 16 ulp anyway: a 1-ulp approximate reciprocal is enough
-    r.ix = __frcp_rn(r.dx); r.iy = __frcp_rn(r.dy); r.iz = __frcp_rn(r.dz);
-#else
-    r.ix = 1.0f / r.dx; r.iy = 1.0f / r.dy; r.iz = 1.0f / r.dz;
-#endif
+    const float tiny = 1e-18f;
+    const float bdx = fabsf(r.dx) < tiny ? copysignf(tiny, r.dx) : r.dx;
+    const float bdy = fabsf(r.dy) < tiny ? copysignf(tiny, r.dy) : r.dy;
+    const float bdz = fabsf(r.dz) < tiny ? copysignf(tiny, r.dz) : r.dz;
+    r.ix = 1.0f / bdx; r.iy = 1.0f / bdy; r.iz = 1.0f / bdz;
     const float ulp16 = 16.0f * 5.9604645e-08f;
     float px = ulp16 * (fabsf(r.ox) + pad_scale[0]) * fabsf(r.ix);
     float py = ulp16 * (fabsf(r.oy) + pad_scale[1]) * fabsf(r.iy);
@@ -111,9 +121,9 @@ __device__ __forceinline__ RaySetup make_ray(float4 o4, float4 d4, const float* 
     r.nx = bx - px; r.fx = bx + px;
     r.ny = by - py; r.fy = by + py;
     r.nz = bz - pz; r.fz = bz + pz;
-    r.sx = r.dx < 0.0f ? 1 : 0;
-    r.sy = r.dy < 0.0f ? 3 : 2;
-    r.sz = r.dz < 0.0f ? 5 : 4;
+    r.sx = bdx < 0.0f ? 1 : 0; // (-0.0 counts as negative, like the clamped reciprocal)
+    r.sy = bdy < 0.0f ? 3 : 2;
+    r.sz = bdz < 0.0f ? 5 : 4;
     return r;
 }
 
@@ -157,7 +167,6 @@ __device__ __forceinline__ bool tri_uv(const RaySetup& r, float4 a, float4 b, fl
 
 } // namespace ort
 #include "traverse.cuh"
-#include "traverse_pool.cuh"
 namespace ort {
 
 // ------------------------------------------------------------------------------------------------

@@ -105,13 +105,6 @@ struct ort_ctx {
     size_t pinned_bytes = 0;
 
     int trace_grid[2] = {0, 0}; // persistent grid sizes: closest hit, light sum
-#ifndef ORT_TRACE_POOL
-#define ORT_TRACE_POOL 0
-#endif
-    int use_pool = ORT_TRACE_POOL; // k_trace_pool (traverse_pool.cuh) instead of k_trace
-    int pool_grid[2] = {0, 0};
-    uint2* pool_overflow = nullptr; // deep stack entries of the pool kernels: POOL * POOL_OVF per warp of the larger grid
-    int pool_refill = 12, pool_node_min = 24, pool_inner_min = 20;
     int shade_grid = 0;
     // tuning knobs: fixed at their measured optimum in the shipped library; a -DORT_TUNING build
     // (make variant) reads them from the environment for tools/tune.py
@@ -446,19 +439,6 @@ void launch_trace(ort_ctx* ctx, ort_ctx::PathSet& P, cudaStream_t st, const floa
     a.qo = qo; a.qd = qd; a.n_ptr = n_ptr; a.work_ctr = work_ctr; a.index = index;
     a.hits = P.hits; a.lsum = lsum ? lsum : P.lsum;
     a.refill_threshold = ctx->refill; a.inner_min = ctx->inner_min;
-    if (ctx->use_pool) {
-        PoolArgs pa;
-        // every pipeline (stream) owns its own slice of the overflow scratch: concurrent launches never share one
-        const size_t per_launch = (size_t)std::max(ctx->pool_grid[0], ctx->pool_grid[1]) * POOL_WARPS * POOL * POOL_OVF;
-        int pipe = 0;
-        for (int i = 1; i < MAX_PIPES; i++) if (st == ctx->aux_stream[i]) pipe = i;
-        pa.overflow = ctx->pool_overflow + per_launch * (size_t)pipe;
-        pa.refill_min = ctx->pool_refill; pa.node_min = ctx->pool_node_min; pa.inner_min = ctx->pool_inner_min;
-        if (mode == 0) k_trace_pool<false><<<ctx->pool_grid[0], TRACE_THREADS, sizeof(PoolWarp<false>) * POOL_WARPS, st>>>(ctx->sd, a, pa);
-        else k_trace_pool<true><<<ctx->pool_grid[1], TRACE_THREADS, sizeof(PoolWarp<true>) * POOL_WARPS, st>>>(ctx->sd, a, pa);
-        ctx->launches++;
-        return;
-    }
     if (mode == 0) k_trace<false><<<ctx->trace_grid[0], TRACE_THREADS, 0, st>>>(ctx->sd, a);
     else k_trace<true><<<ctx->trace_grid[1], TRACE_THREADS, 0, st>>>(ctx->sd, a);
     ctx->launches++;
@@ -749,10 +729,6 @@ int ort_create(ort_ctx** out, const ort_device_cfg* cfg) {
     if (const char* e2 = std::getenv("ORT_OVERLAP")) c->overlap = std::atoi(e2);
     if (const char* e2 = std::getenv("ORT_WAVE_PATHS")) c->capacity_cfg = std::atoll(e2);
 #ifdef ORT_TUNING
-    if (const char* e2 = std::getenv("ORT_POOL")) c->use_pool = std::atoi(e2);
-    if (const char* e2 = std::getenv("ORT_POOL_REFILL")) c->pool_refill = std::atoi(e2);
-    if (const char* e2 = std::getenv("ORT_POOL_NODE_MIN")) c->pool_node_min = std::atoi(e2);
-    if (const char* e2 = std::getenv("ORT_POOL_INNER_MIN")) c->pool_inner_min = std::atoi(e2);
     if (const char* e2 = std::getenv("ORT_REFILL")) c->refill = std::atoi(e2);
     if (const char* e2 = std::getenv("ORT_INNER_MIN")) c->inner_min = std::atoi(e2);
     if (const char* e2 = std::getenv("ORT_TILED")) c->tiled = std::atoi(e2);
@@ -787,17 +763,6 @@ int ort_create(ort_ctx** out, const ort_device_cfg* cfg) {
     c->trace_grid[0] = c->sm_count * std::max(occ, 1);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<true>, TRACE_THREADS, 0);
     c->trace_grid[1] = c->sm_count * std::max(occ, 1);
-    if (c->use_pool) {
-        const size_t sm0 = sizeof(PoolWarp<false>) * POOL_WARPS, sm1 = sizeof(PoolWarp<true>) * POOL_WARPS;
-        cudaFuncSetAttribute(k_trace_pool<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm0);
-        cudaFuncSetAttribute(k_trace_pool<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_pool<false>, TRACE_THREADS, sm0);
-        c->pool_grid[0] = c->sm_count * std::max(occ, 1);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_pool<true>, TRACE_THREADS, sm1);
-        c->pool_grid[1] = c->sm_count * std::max(occ, 1);
-        const size_t bytes = (size_t)std::max(c->pool_grid[0], c->pool_grid[1]) * POOL_WARPS * POOL * POOL_OVF * sizeof(uint2) * MAX_PIPES;
-        if ((e = cudaMalloc(&c->pool_overflow, bytes)) != cudaSuccess) return bail("cudaMalloc (pool overflow)", e);
-    }
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shade, 256, 0);
     c->shade_grid = c->sm_count * std::max(occ, 1);
     *out = c;
@@ -817,7 +782,6 @@ void ort_destroy(ort_ctx* ctx) {
         if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
     }
     if (ctx->d_stats) cudaFree(ctx->d_stats);
-    if (ctx->pool_overflow) cudaFree(ctx->pool_overflow);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->frame) cudaFree(ctx->frame);
     if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }

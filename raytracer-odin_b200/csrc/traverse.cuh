@@ -72,6 +72,18 @@ namespace ort {
         da = td_; ca = tc_;                     \
     }
 
+// Triangle records are read once per leaf visit: they bypass L1 allocation and leave the L1 to the nodes
+// (+0.7 % on C2 and C4; a prefetch of the leaf's first triangle line while the lane waits for the others to finish
+// descending was 3-5 % slower: profiles/r2_traversal_round2.md).
+__device__ __forceinline__ F8 ldg8_noalloc(const void* p) {
+    F8 r;
+    asm("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w)
+        : "l"(p));
+    return r;
+}
+#define ORT_LDG8_TRI(P) ldg8_noalloc(P)
+
 struct TraceArgs {
     const float4* qo;       // ray origins (xyz) + path slot (w), compacted queue order
     const float4* qd;       // ray directions
@@ -185,7 +197,7 @@ k_trace(const SceneDev s, const TraceArgs a) {
                         // cast_ray_through_trigs (raytracer.odin:351-369): reference order, first wins ties
                         for (uint32_t i = 0; i < cnt; i++) {
                             const float4* tp = s.tris + (size_t)(first + i) * 4;
-                            const F8 tab = ldg8(tp);
+                            const F8 tab = ORT_LDG8_TRI(tp);
                             const float4 ta = tab.lo, tb = tab.hi, tc = ldg4(tp + 2);
                             float id, bx, by, bz, t, a00, a10;
                             tri_det_t(r, ta, tb, tc, id, bx, by, bz, t, a00, a10);
@@ -202,7 +214,7 @@ k_trace(const SceneDev s, const TraceArgs a) {
                         // returns t = -1 when (u,v) is outside, then `!(t >= 0)` skips
                         for (uint32_t i = 0; i < cnt; i++) {
                             const float4* tp = s.tris + (size_t)(first + i) * 4;
-                            const F8 tab = ldg8(tp);
+                            const F8 tab = ORT_LDG8_TRI(tp);
                             const float4 ta = tab.lo, tb = tab.hi, tc = ldg4(tp + 2);
                             float id, bx, by, bz, t, a00, a10, u, v;
                             tri_det_t(r, ta, tb, tc, id, bx, by, bz, t, a00, a10);

@@ -460,6 +460,53 @@ def test_deep_bvh_reference_stack_need(orc):
           f"faithful {cf['node_pops'] / m:.0f} vs ideal {ci['node_pops'] / m:.0f} node pops per ray; hit fraction {(g['tri'] >= 0).mean():.2f}")
 
 
+def test_zero_and_tiny_direction_components(scenes, orc):
+    """Rays with a direction component that is exactly 0, -0, denormal or tiny (an axis-aligned camera produces a few
+    exact zeros per wave by cancellation in pixel_to_ray_dir): the reference's slab test divides by it and gets an
+    unbounded or an empty interval; the library clamps |d| for its box tests (kernels.cuh make_ray).  Hits must
+    equal the faithful oracle bit for bit, and such a ray must not degenerate into a walk over the whole tree
+    (measured before the fix: 1.2-2.0 ms for ONE ray on the 1 M-triangle scene)."""
+    from raytracer_odin_b200 import cabi
+
+    scene = scenes("terrain_c4", 1920, 1080)
+    o = orc.OracleScene(scene)
+    rng = np.random.default_rng(12)
+    n = 6000
+    rays = np.zeros(n, cabi.RAY_DTYPE)
+    rays["o"] = rng.uniform(-40, 40, (n, 3)).astype(np.float32)
+    rays["o"][:, 1] = rng.uniform(-3, 20, n).astype(np.float32)
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d = d.astype(np.float32)
+    special = np.float32([0.0, -0.0, 1e-30, -1e-30, 1e-42, -1e-42, 1e-19, -1e-19, 1e-17, -1e-17])
+    for k in range(n):
+        ax = k % 3
+        d[k, ax] = special[(k // 3) % len(special)]
+        if k % 7 == 0:  # two degenerate components
+            d[k, (ax + 1) % 3] = special[(k // 21) % len(special)]
+        rest = [a for a in range(3) if abs(d[k, a]) > 1e-10]
+        d[k, rest] /= np.float32(np.linalg.norm(d[k, rest]))
+    rays["d"] = d
+    # the camera-like cases of the benchmark scene: origin on the axis, component exactly zero
+    rays["o"][:8] = np.float32([0.0, 16.0, 62.0])
+    rays["d"][0] = np.float32([0.0, -0.5062409043312073, -0.8623921275138855])
+    rays["d"][1] = np.float32([0.35083362460136414, 0.0, -0.9364379048347473])
+    rays["d"][2] = np.float32([-0.0, -0.5062409043312073, -0.8623921275138855])
+    rays["d"][3] = np.float32([0.35083362460136414, -0.0, -0.9364379048347473])
+    ref, c = o.trace_rays(rays, mode=0, threads=orc.load().orc_hardware_threads())
+    flags = o.ties.copy()
+    with _renderer(scene) as r:
+        g = r.trace_rays(rays)
+        ms_special = r.bench_trace(rays[:4], 0, 3)
+        generic = rays[:4].copy()
+        generic["d"] = np.float32([[0.01, -0.506, -0.8624], [0.35, 0.01, -0.9364], [-0.01, -0.506, -0.8624], [0.35, -0.01, -0.9364]])
+        ms_generic = r.bench_trace(generic, 0, 3)
+    _hits_equal_flags(g, ref, flags, "zero direction components", max_tie_frac=1e-2)
+    assert (ref["tri"] >= 0).mean() > 0.2
+    print(f"4 camera rays with an exactly-zero component: {ms_special:.3f} ms per launch; 4 generic neighbours: {ms_generic:.3f} ms")
+    assert ms_special < 10 * ms_generic + 0.05, (ms_special, ms_generic)
+
+
 # ------------------------------------------------------------------------------------------------
 # radiance at BASELINE sizes
 # ------------------------------------------------------------------------------------------------
