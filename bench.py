@@ -122,16 +122,15 @@ def cpu_leg(scene, cfg, target_s):
     w, h, depth = cfg["width"], cfg["height"], cfg["ray_depth"]
     nat = orc.OracleScene(scene, native=True)
     threads = max(1, nat.lib.orc_hardware_threads())
-    spp = 4
-    # pilot: every 32nd tile (~1/1024 of the frame), 1 spp
+    # pilot: every 16th tile in x and y (1/256 of the frame), 1 spp -> size the sample for ~target_s of wall time
     t0 = time.perf_counter()
-    _, c = nat.render(w, h, depth, 1, seed=SEED, mode=0, schedule=0, threads=threads, tile_stride=32)
+    _, c = nat.render(w, h, depth, 1, seed=SEED, mode=0, schedule=0, threads=threads, tile_stride=16)
     pilot_s = max(time.perf_counter() - t0, 1e-4)
-    n_tiles = ((w + 3) // 4) * ((h + 3) // 4)
-    rays_per_tile_spp = c["rays"] / max(n_tiles / 1024.0, 1.0)
-    rate = c["rays"] / pilot_s
-    want_tiles = rate * target_s / max(rays_per_tile_spp * spp, 1e-9)
-    stride = int(max(1, min(32, round((n_tiles / max(want_tiles, 1.0)) ** 0.5))))
+    full_frame_1spp_s = pilot_s * 256.0          # the whole frame at 1 spp at the pilot's rate
+    spp = 4
+    stride = int(max(1, min(16, round((full_frame_1spp_s * spp / target_s) ** 0.5))))
+    if stride == 1:                               # even the whole frame is too short: more samples per pixel
+        spp = int(max(4, min(64, round(target_s / full_frame_1spp_s))))
 
     def run(mode=0):
         t0 = time.perf_counter()
@@ -139,7 +138,7 @@ def cpu_leg(scene, cfg, target_s):
         dt = time.perf_counter() - t0
         return c["rays"] / dt / 1e6, c, dt
 
-    sample = (f"rate on a sample: every {stride}th 4x4-pixel tile in x and y over the whole {w}x{h} frame "
+    sample = (f"rate on a sample: one 4x4-pixel tile of every {stride}x{stride} tiles over the whole {w}x{h} frame "
               f"(1/{stride * stride} of the pixels), {spp} spp, depth {depth}")
     return run, threads, sample, nat
 
