@@ -389,24 +389,39 @@ def main():
         # is the box's L2 read bandwidth, measured here with the library's streaming-read probe on a working set
         # of the scene's size (at least 32 MB to stay out of L1); C5 (2.3 GB) streams from HBM
         ws = ps["wide_nodes"] * 128 + ps["light_wide_nodes"] * 128 + (len(scene.triangles) + len(scene.light_triangles)) * 64
-        l2_bound = ws < L2_RESIDENT_BYTES
-        probe = max(ws, 32 << 20) if l2_bound else min(max(ws, 1 << 30), 4 << 30)
+        alg_per_launch = (bpr * ps["rays_traced"] / n_launch) if bpr else None
+        # ... or whose MEASURED DRAM traffic (ncu) is a small part of the algorithmic bytes: C5's 2.3 GB do not fit the
+        # L2, but its hot upper levels do — ncu shows ~2 GB of DRAM traffic per launch against ~14 GB algorithmic
+        served_by_l2 = traffic is not None and alg_per_launch is not None and traffic < 0.25 * alg_per_launch
+        if achieved is not None and achieved > hbm_peak:  # more algorithmic bytes per second than HBM can deliver:
+            served_by_l2 = True                            # they cannot be streaming from HBM
+        l2_bound = ws < L2_RESIDENT_BYTES or served_by_l2
+        probe = min(max(ws, 32 << 20), 96 << 20) if l2_bound else min(max(ws, 1 << 30), 4 << 30)
         read_gbs = r.bench_read_bw(probe, 20 if probe <= (256 << 20) else 5)
         if l2_bound:
             peak, peak_src = read_gbs, ("measured in this run: ort_bench_read_bw (256-bit read-only loads from all SMs) over "
-                                        f"a {probe >> 20} MB working set = L2 read bandwidth")
+                                        f"a {probe >> 20} MB working set = L2 read bandwidth"
+                                        + ("" if ws < L2_RESIDENT_BYTES else
+                                           f"; the {ws >> 20} MB working set exceeds the L2, but "
+                                           + (f"ncu's DRAM traffic per launch is {traffic / alg_per_launch:.0%} of the algorithmic bytes"
+                                              if traffic else "the algorithmic rate exceeds the HBM copy peak")
+                                           + ": the traversal is served by the L2 (hot upper levels of the tree)"))
         else:
             peak, peak_src = hbm_peak, hbm_src
         roof = {"bound": "l2" if l2_bound else "hbm", "kernel": "k_trace<closest>", "unit": "GB/s",
                 "achieved": achieved, "peak": peak, "frac": (achieved / peak) if achieved else None,
                 "peak_source": peak_src, "traffic": traffic,
-                "working_set_bytes": int(ws), "hbm_peak": hbm_peak, "hbm_read_probe_gbs": None if l2_bound else read_gbs,
+                "working_set_bytes": int(ws),
+                "hbm": {"peak": hbm_peak, "peak_source": hbm_src, "unit": "GB/s",
+                        "achieved": (traffic / (ps["trace_ms"] / n_launch * 1e-3) / 1e9) if traffic else None,
+                        "frac": (traffic / (ps["trace_ms"] / n_launch * 1e-3) / 1e9 / hbm_peak) if traffic else None,
+                        "what": "MEASURED DRAM bytes per launch (ncu, profiles/ncu_traffic_*.json) / average launch time of this run"},
                 "bytes_per_ray": bpr, "n_box": counts["n_box"] if counts else None,
                 "n_tri": counts["n_tri"] if counts else None,
                 "profiled_pass": f"{prof_spp} spp ({n_launch // depth} waves of {spp_per_wave} spp), kernel classes serialised",
                 "rays_per_pass": ps["rays_traced"], "launches_per_pass": n_launch,
                 "kernel_ms_per_pass": ps["trace_ms"], "avg_launch_ms": ps["trace_ms"] / n_launch,
-                "algorithmic_bytes_per_launch": (bpr * ps["rays_traced"] / n_launch) if bpr else None,
+                "algorithmic_bytes_per_launch": alg_per_launch,
                 "trace_grays_per_s": ps["rays_traced"] / trace_s / 1e9,
                 "pass_breakdown_ms": {"trace": ps["trace_ms"], "light": ps["light_ms"], "shade": ps["shade_ms"],
                                       "other": ps["other_ms"]},

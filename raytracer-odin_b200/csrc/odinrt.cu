@@ -821,6 +821,7 @@ int upload_scene_impl(ort_ctx* ctx, const ort_scene* sc, SharedWide* shared) {
     if (!sc) return fail(ctx, "ort_upload_scene: scene is NULL");
     Bind b(ctx->device);
     PhaseTimer pt("ort_upload_scene");
+    if (join_pipes(ctx)) return 1; // chained waves of a frame may still be reading the scene on the other pipelines
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->has_scene = false;
     ctx->scene_bytes = 0;

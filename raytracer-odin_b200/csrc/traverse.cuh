@@ -3,9 +3,12 @@
 // (surface_sampling_pdf_bvh_sum, shading.odin:62-94).
 //
 // Design notes (every choice below was measured on B200, see profiles/):
-//   * Software BVH traversal here is ISSUE bound, not bandwidth bound (DRAM < 4 %, L2 ~ 12 % of
-//     peak, issue slots ~ 70 % busy), and its enemy is SIMD divergence: the first version (warp
-//     fetches 32 rays, runs until the slowest is done) executed with 6 of 32 lanes active.
+//   * Software BVH traversal here is not bandwidth bound (DRAM < 4 %, L2 ~ 20-30 % of peak).  The first
+//     version (warp fetches 32 rays, runs until the slowest is done) executed with 6 of 32 lanes active and
+//     was issue bound; with the scheduling below the kernel is LATENCY bound at the knee of its occupancy
+//     curve: throughput follows the number of node fetches in flight per SM (warps x descending lanes).
+//     Denser lanes alone do not help — a warp-level ray pool with dense node / leaf phases was level with
+//     this kernel at equal occupancy (profiles/r2_pool_traversal.md).
 //   * Persistent threads with PER-LANE dynamic fetch: when fewer than `refill_threshold` lanes of
 //     a warp still hold a ray, the warp leaves the traversal loop (in-flight rays keep their state
 //     in registers and on the stack), idle lanes claim new rays from the compacted queue with ONE
