@@ -1,4 +1,5 @@
 O=gpurun_out
+# everything measured at the end of round 2, in one GPU call (outputs in gpurun_out/, copied to profiles/)
 python -m pytest tests -m gpu -q 2>&1 | tail -6 > $O/r2j_tests.log
 python bench.py --steps 20 --warmup 5 > $O/r2j_bench_c4.json 2> $O/r2j_bench_c4.err
 python bench.py --config C5 --bvh device --steps 3 --warmup 3 --spp 64 > $O/r2j_bench_c5.json 2> $O/r2j_bench_c5.err
