@@ -729,15 +729,7 @@ int ort_create(ort_ctx** out, const ort_device_cfg* cfg) {
     if (const char* e2 = std::getenv("ORT_OVERLAP")) c->overlap = std::atoi(e2);
     if (const char* e2 = std::getenv("ORT_WAVE_PATHS")) c->capacity_cfg = std::atoll(e2);
 #ifdef ORT_TUNING
-    if (const char* e2 = std::getenv("ORT_REFILL")) c->refill = std::atoi(e2);
-    if (const char* e2 = std::getenv("ORT_INNER_MIN")) c->inner_min = std::atoi(e2);
-    if (const char* e2 = std::getenv("ORT_TILED")) c->tiled = std::atoi(e2);
-    if (const char* e2 = std::getenv("ORT_TILE")) {
-        int a_ = 2, b_ = 2, c_ = 8;
-        if (std::sscanf(e2, "%dx%dx%d", &a_, &b_, &c_) == 3 && a_ * b_ * c_ == 32) { c->tile_w = a_; c->tile_h = b_; c->tile_s = c_; }
-    }
-    if (const char* e2 = std::getenv("ORT_LIGHT_PREFILTER")) c->light_prefilter = std::atoi(e2);
-    if (const char* e2 = std::getenv("ORT_BIN")) c->bin_octants = std::atoi(e2);
+#include "tuning_env.inl" // make variant EXTRA=-DORT_TUNING: knobs from the environment for tools/tune.py
 #endif
     ctx = c;
     auto bail = [&](const char* what, cudaError_t err) {
