@@ -255,14 +255,18 @@ int main(int argc, char** argv) {
     } else {
         const long trials = a.times > 0 ? a.times : 1;
         std::vector<double> timings;
+        uint64_t last_done = 0;
         for (long trial = 0; trial < trials; trial++) { // render_scene (raytracer.odin:606-624): trials replay the same samples
             t0 = now_s();
-            frame_render(first, (uint64_t)std::max(0L, a.num_samples));
+            last_done = frame_render(first, (uint64_t)std::max(0L, a.num_samples));
             frame_wait();
             timings.push_back(now_s() - t0);
             std::printf("Trial %ld >>> Rendered in %.3fms\n", trial, timings.back() * 1e3);
         }
-        first += (uint64_t)std::max(0L, a.num_samples);
+        // one GPU renders a contiguous prefix, so an interrupted run resumes exactly where it stopped; several GPUs leave
+        // gaps inside their blocks: the whole range counts as consumed (no index is ever rendered twice; the per-pixel
+        // count in the checkpoint says how many samples the image really holds)
+        first += (ctx && g_interrupt) ? last_done : (uint64_t)std::max(0L, a.num_samples);
         ort_stats st{};
         if (ctx) ort_get_stats(ctx, &st); else ort_multi_get_stats(multi, &st);
         double total = 0;
