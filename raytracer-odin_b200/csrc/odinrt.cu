@@ -1520,6 +1520,10 @@ int ensure_rbuf(ort_multi* m, size_t npix) {
 int multi_snapshot(ort_multi* m) {
     const int G = (int)m->ctx.size();
     const size_t npix = (size_t)m->fw * m->fh;
+    if (m->rstream) { // an earlier snapshot's reduce may still be reading the per-GPU snapshot buffers
+        Bind b(m->ctx[0]->device);
+        cudaStreamSynchronize(m->rstream);
+    }
     for (int g = 0; g < G; g++) {
         ort_ctx* ctx = m->ctx[g];
         Bind b(ctx->device);
