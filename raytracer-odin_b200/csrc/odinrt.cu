@@ -112,7 +112,8 @@ struct ort_ctx {
     int tile_w = 2, tile_h = 2, tile_s = 8;
     int bin_octants = 1;     // 0: plain per-warp queue compaction (no direction-octant binning)
     int light_prefilter = 1; // 0: send every continuation ray through the light pass
-    int refill = ORT_REFILL_THRESHOLD; // dynamic-fetch threshold
+    int refill = ORT_REFILL_THRESHOLD; // dynamic-fetch threshold of the closest-hit pass
+    int refill_light = ORT_REFILL_LIGHT; // ... of the light pass
     int inner_min = ORT_INNER_MIN;     // inner-loop early-exit threshold
     bool profiling = false;
     double ms_trace = 0, ms_light = 0, ms_shade = 0, ms_other = 0, ms_render = 0;
@@ -438,7 +439,7 @@ void launch_trace(ort_ctx* ctx, ort_ctx::PathSet& P, cudaStream_t st, const floa
     TraceArgs a;
     a.qo = qo; a.qd = qd; a.n_ptr = n_ptr; a.work_ctr = work_ctr; a.index = index;
     a.hits = P.hits; a.lsum = lsum ? lsum : P.lsum;
-    a.refill_threshold = ctx->refill; a.inner_min = ctx->inner_min;
+    a.refill_threshold = mode == 0 ? ctx->refill : ctx->refill_light; a.inner_min = ctx->inner_min;
     if (mode == 0) k_trace<false><<<ctx->trace_grid[0], TRACE_THREADS, 0, st>>>(ctx->sd, a);
     else k_trace<true><<<ctx->trace_grid[1], TRACE_THREADS, 0, st>>>(ctx->sd, a);
     ctx->launches++;

@@ -41,8 +41,14 @@
 
 namespace ort {
 
+// Dynamic-fetch thresholds, re-tuned in round 2 after the zero-component fix (profiles/r2m_refill_sweep.md): the
+// closest-hit pass refills when fewer than 16 lanes hold a ray (C2 +3.3 %, C4 +2.5 % over 22), the all-hit light pass
+// keeps 22.
 #ifndef ORT_REFILL_THRESHOLD
-#define ORT_REFILL_THRESHOLD 22
+#define ORT_REFILL_THRESHOLD 16
+#endif
+#ifndef ORT_REFILL_LIGHT
+#define ORT_REFILL_LIGHT 22
 #endif
 #ifndef ORT_INNER_MIN
 #define ORT_INNER_MIN 12
@@ -53,6 +59,7 @@ namespace ort {
 // separate validity compare is needed.
 
 // Stack entry = (node reference, entry distance bits): one 64-bit access per push / pop.
+#if ORT_SMEM_STACK > 0
 #define ORT_PUSH(NODE, DIST)                                                                          \
     {                                                                                                 \
         const uint2 e_ = make_uint2((uint32_t)(NODE), __float_as_uint(DIST));                         \
@@ -66,6 +73,19 @@ namespace ort {
         const uint2 e_ = sp < SMEM_STACK ? sh_stack[sp][threadIdx.x] : l_stack[sp - SMEM_STACK];      \
         NODE = (int)e_.x; DIST = __uint_as_float(e_.y);                                               \
     }
+#else // experiment: the whole stack in thread-local memory (L1-cached), no shared memory, no split
+#define ORT_PUSH(NODE, DIST)                                                                          \
+    {                                                                                                 \
+        l_stack[sp] = make_uint2((uint32_t)(NODE), __float_as_uint(DIST));                            \
+        sp++;                                                                                         \
+    }
+#define ORT_POP(NODE, DIST)                                                                           \
+    {                                                                                                 \
+        sp--;                                                                                         \
+        const uint2 e_ = l_stack[sp];                                                                 \
+        NODE = (int)e_.x; DIST = __uint_as_float(e_.y);                                               \
+    }
+#endif
 #define ORT_CSWAP(da, ca, db, cb)               \
     {                                           \
         const bool sw_ = db < da;               \
@@ -104,7 +124,9 @@ struct TraceArgs {
 template <bool LIGHT>
 __global__ void __launch_bounds__(TRACE_THREADS, ORT_TRACE_MIN_CTAS)
 k_trace(const SceneDev s, const TraceArgs a) {
+#if ORT_SMEM_STACK > 0
     __shared__ uint2 sh_stack[SMEM_STACK][TRACE_THREADS];
+#endif
     uint2 l_stack[LOCAL_STACK];
 
     const uint32_t n = *a.n_ptr;

@@ -1,6 +1,7 @@
 // tuning_env.inl — included by ort_create only in -DORT_TUNING builds (make variant): the traversal / queue knobs
 // that are fixed at their measured optimum in the shipped library, read from the environment for tools/tune.py.
     if (const char* e2 = std::getenv("ORT_REFILL")) c->refill = std::atoi(e2);
+    if (const char* e2 = std::getenv("ORT_REFILL_LIGHT")) c->refill_light = std::atoi(e2);
     if (const char* e2 = std::getenv("ORT_INNER_MIN")) c->inner_min = std::atoi(e2);
     if (const char* e2 = std::getenv("ORT_TILED")) c->tiled = std::atoi(e2);
     if (const char* e2 = std::getenv("ORT_TILE")) {
