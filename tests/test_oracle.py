@@ -370,3 +370,36 @@ def test_strided_tile_sample_is_a_subset_of_the_frame(scenes):
     assert np.array_equal(part[sel], full[sel])
     assert np.all(part["count"][~sel] == 0)
     assert 0 < cp["rays"] < cf["rays"]
+
+
+def test_check_intersect_ray_aabb_zero_direction_components():
+    """SURVEY §8(c) fixture (1), `d_i = 0`: the reference divides by d (raytracer.odin:125-126), so a zero component
+    gives an unbounded slab interval when the origin lies inside that slab and an empty one otherwise — also for -0.0.
+    (The GPU's box test clamps |d| instead and must stay a superset: tests/test_gpu_round2.py.)"""
+    lib = orc.load()
+    t = C.c_float()
+    lo, hi = [-1.0, -1.0, -1.0], [1.0, 1.0, 1.0]
+    inf = np.float32(np.inf)
+    for zero in (0.0, -0.0):
+        # origin inside the x slab, travelling along +z towards the box: hit at z distance 2
+        assert lib.orc_check_intersect_ray_aabb(fp([0.5, 0.2, -3]), fp([zero, 0.0, 1.0]), fp(lo), fp(hi), inf, C.byref(t))
+        assert t.value == 2
+        # origin outside the x slab: never hit, whatever the other axes say
+        assert not lib.orc_check_intersect_ray_aabb(fp([1.5, 0.2, -3]), fp([zero, 0.0, 1.0]), fp(lo), fp(hi), inf, C.byref(t))
+        # two zero components, origin inside both slabs, box behind the origin: rejected by t2 < 0
+        assert not lib.orc_check_intersect_ray_aabb(fp([0.5, 0.2, 3]), fp([zero, zero, 1.0]), fp(lo), fp(hi), inf, C.byref(t))
+    # the benchmark camera's degenerate rays (profiles/r2_zero_direction_components.md) against the C4 root box
+    root_lo, root_hi = [-50.0, -6.262298, -50.0], [50.0, 12.434973, 50.0]
+    assert lib.orc_check_intersect_ray_aabb(fp([0, 16, 62]), fp([0.0, -0.5062409043312073, -0.8623921275138855]), fp(root_lo), fp(root_hi), inf, C.byref(t))
+    assert not lib.orc_check_intersect_ray_aabb(fp([0, 16, 62]), fp([0.35083362460136414, 0.0, -0.9364379048347473]), fp(root_lo), fp(root_hi), inf, C.byref(t))
+
+
+def test_c1_golden_at_baseline_size(scenes):
+    """SURVEY §8(c) fixture (6): the C1 Cornell image at its BASELINE size (256x256, depth 6, 64 spp), committed as raw
+    f32 totals (tests/golden/cornell_c1_256.npz) — the end-to-end regression pin of the oracle; the GPU is held
+    against the same file in tests/test_gpu_round2.py."""
+    g = np.load(os.path.join(GOLD, "cornell_c1_256.npz"))
+    s = scenes("cornell", 256, 256)
+    px, c = orc.OracleScene(s).render(256, 256, 6, 64, seed=int(g["seed"]), mode=0, schedule=1, threads=8)
+    assert np.all(px["count"] == 64) and c["rays"] == int(g["n_rays"][0])
+    assert px["total"].tobytes() == g["total"].tobytes()
