@@ -332,7 +332,7 @@ int64_t reference_stack_need(const ort_bvh_node* bvh, int64_t n_nodes) {
     return 2 * (int64_t)branches[(size_t)n_nodes - 1] + 1;
 }
 
-void make_isect_records(const ort_triangle* tris, int64_t n, TriIsect* out) {
+void make_isect_records(const ort_triangle* tris, int64_t n, TriIsect* out, bool light) {
     for (int64_t i = 0; i < n; i++) {
         const ort_triangle& t = tris[i];
         TriIsect r;
@@ -344,21 +344,17 @@ void make_isect_records(const ort_triangle* tris, int64_t n, TriIsect* out) {
         r.c0 = +(r.uy * r.vz - r.uz * r.vy);
         r.c1 = -(r.ux * r.vz - r.uz * r.vx);
         r.c2 = +(r.ux * r.vy - r.uy * r.vx);
-        r.pad[0] = r.pad[1] = r.pad[2] = r.pad[3] = 0.0f;
+        r.light[0] = r.light[1] = r.light[2] = r.light[3] = 0.0f;
+        if (light) {
+            // 2 / linalg.length(linalg.cross(trig.u, trig.v))   shading.odin:57
+            float cx = t.u[1] * t.v[2] - t.u[2] * t.v[1];
+            float cy = t.u[2] * t.v[0] - t.u[0] * t.v[2];
+            float cz = t.u[0] * t.v[1] - t.u[1] * t.v[0];
+            float len = std::sqrt(cx * cx + cy * cy + cz * cz);
+            r.light[0] = t.ng[0]; r.light[1] = t.ng[1]; r.light[2] = t.ng[2];
+            r.light[3] = 2.0f / len;
+        }
         out[i] = r;
-    }
-}
-
-void make_light_records(const ort_triangle* tris, int64_t n, TriLight* out) {
-    for (int64_t i = 0; i < n; i++) {
-        const ort_triangle& t = tris[i];
-        // 2 / linalg.length(linalg.cross(trig.u, trig.v))   shading.odin:57
-        float cx = t.u[1] * t.v[2] - t.u[2] * t.v[1];
-        float cy = t.u[2] * t.v[0] - t.u[0] * t.v[2];
-        float cz = t.u[0] * t.v[1] - t.u[1] * t.v[0];
-        float len = std::sqrt(cx * cx + cy * cy + cz * cz);
-        out[i].ng[0] = t.ng[0]; out[i].ng[1] = t.ng[1]; out[i].ng[2] = t.ng[2];
-        out[i].k = 2.0f / len;
     }
 }
 

@@ -21,6 +21,12 @@ constexpr float TAU_F = 6.28318530717958647692528676655900576f;
 #ifndef ORT_SMEM_STACK
 #define ORT_SMEM_STACK 16
 #endif
+// k_trace<light> is compiled for 8 resident CTAs per SM (63 registers, no spills; the closest-hit kernel stays at
+// its own 69 / 7 CTAs, where 8 was slower): 7 -> 8 CTAs is -3.4 % light-pass time, 9 and 10 lose again
+// (profiles/r2s_light_pass.md)
+#ifndef ORT_LIGHT_MIN_CTAS
+#define ORT_LIGHT_MIN_CTAS 8
+#endif
 #ifndef ORT_TRACE_MIN_CTAS
 #define ORT_TRACE_MIN_CTAS 1
 #endif
@@ -48,7 +54,6 @@ struct SceneDev {
     const float4* nodes;  // WideNode[], 8 float4 each: scene BVH (root 0) followed by the light BVH
     const float4* tris;   // TriIsect[], 4 float4 (64 B) each: scene triangles followed by the light triangles
     const float4* ltris;  // = tris + 4 * light_tri_base (light sampling, shading.odin:41-50)
-    const float4* llight; // TriLight[], indexed by light triangle
     int32_t light_root;       // node index of the light BVH root inside `nodes`
     uint32_t light_tri_base;  // index of the first light triangle inside `tris`
     const float4* tshade; // TriShade[], 4 float4 each
@@ -412,26 +417,30 @@ __device__ __forceinline__ float4 env_lookup(const SceneDev& s, float dx, float 
 // ------------------------------------------------------------------------------------------------
 // Can the ray reach ANY light?  Same conservative slab test as the traversal, applied to the (up
 // to four) child boxes of the light BVH's root.  Rays that fail have a light-pdf sum of exactly 0
-// (surface_sampling_pdf_bvh_sum never gets past shading.odin:86-89) and skip the light pass.
-__device__ __forceinline__ bool light_root_hit(const SceneDev& s, float4 o4, float4 d4) {
+// (surface_sampling_pdf_bvh_sum never gets past shading.odin:86-89) and skip the light pass.  The
+// result is the 4-bit mask of the root's children whose boxes the ray enters: it travels with the
+// ray's light-queue entry (bits 28..31, LQ_MASK_SHIFT), and k_trace<light> starts at those children
+// instead of visiting the root a second time — for most candidates that is one of two or three node
+// round trips (profiles/r2r_light_skip_root.md).
+__device__ __forceinline__ unsigned light_root_mask(const SceneDev& s, float4 o4, float4 d4) {
     const RaySetup r = make_ray(o4, d4, s.pad_scale);
     const float4* nd = s.nodes + (size_t)s.light_root * 8;
     const float4 nxp = ldg4(nd + r.sx), fxp = ldg4(nd + (r.sx ^ 1));
     const float4 nyp = ldg4(nd + r.sy), fyp = ldg4(nd + (r.sy ^ 1));
     const float4 nzp = ldg4(nd + r.sz), fzp = ldg4(nd + (r.sz ^ 1));
     const int4 ch = __ldg(reinterpret_cast<const int4*>(nd + 6));
-    bool any = false;
-#define ORT_BOX(k, C)                                                                             \
+    unsigned m = 0u;
+#define ORT_BOX(k, C, BIT)                                                                        \
     {                                                                                             \
         const float tn = fmaxf(fmaxf(fmaf(nxp.k, r.ix, r.nx), fmaf(nyp.k, r.iy, r.ny)),           \
                                fmaxf(fmaf(nzp.k, r.iz, r.nz), 0.0f));                             \
         const float tf = fminf(fminf(fmaf(fxp.k, r.ix, r.fx), fmaf(fyp.k, r.iy, r.fy)),           \
                                fmaf(fzp.k, r.iz, r.fz));                                          \
-        any = any || (tn <= tf && C != WIDE_EMPTY);                                               \
+        if (tn <= tf && C != WIDE_EMPTY) m |= BIT;                                                \
     }
-    ORT_BOX(x, ch.x) ORT_BOX(y, ch.y) ORT_BOX(z, ch.z) ORT_BOX(w, ch.w)
+    ORT_BOX(x, ch.x, 1u) ORT_BOX(y, ch.y, 2u) ORT_BOX(z, ch.z, 4u) ORT_BOX(w, ch.w, 8u)
 #undef ORT_BOX
-    return any;
+    return m;
 }
 
 #ifndef ORT_SHADE_MIN_CTAS
@@ -446,7 +455,9 @@ struct ShadeArgs {
     float4* st_c;
     float* lsum_out;
     uint32_t *lq, *lq_count;
-    int bounce, prefilter, bin_octants;
+    int bounce, bin_octants;
+    int prefilter; // 0: every continuation ray is a light candidate; 1: only rays that enter a child box of the light
+                   // root; 2: the same, and the entered children travel with the queue entry (LQ_MASK_SHIFT)
 };
 
 __global__ void __launch_bounds__(256, ORT_SHADE_MIN_CTAS)
@@ -628,7 +639,12 @@ k_shade(const SceneDev s, const RenderParams p, const ShadeArgs a) {
             // traversal warp then share nodes (one L1 wavefront serves several lanes) and child order.
             const int oct = (out_d.x < 0.0f ? 1 : 0) | (out_d.y < 0.0f ? 2 : 0) | (out_d.z < 0.0f ? 4 : 0);
             bool cand = emit && has_lights;
-            if (cand && a.prefilter && !light_root_hit(s, out_o, out_d)) cand = false;
+            unsigned lmask = 0u; // 0 = "start at the root" (no prefilter)
+            if (cand && a.prefilter) {
+                lmask = light_root_mask(s, out_o, out_d);
+                cand = lmask != 0u;
+                if (a.prefilter < 2) lmask = 0u; // positions need all 32 bits: the light pass starts at the root
+            }
             uint32_t rank = 0, lrank = 0;
             if (emit) rank = atomicAdd(&s_cnt[oct], 1u);
             if (cand) lrank = atomicAdd(&s_cnt[8 + oct], 1u);
@@ -648,7 +664,7 @@ k_shade(const SceneDev s, const RenderParams p, const ShadeArgs a) {
                 a.pa_out[q] = out_a;
                 a.pb_out[q] = out_b;
                 if (has_lights) {
-                    if (cand) a.lq[s_off[8 + oct] + lrank] = q;
+                    if (cand) a.lq[s_off[8 + oct] + lrank] = q | (lmask << LQ_MASK_SHIFT);
                     else a.lsum_out[q] = 0.0f;
                 }
             }
@@ -675,14 +691,19 @@ k_shade(const SceneDev s, const RenderParams p, const ShadeArgs a) {
             if (has_lights) {
                 // second queue: only rays that can reach a light need the light-BVH pass
                 bool cand = emit;
-                if (emit && a.prefilter && !light_root_hit(s, out_o, out_d)) { cand = false; a.lsum_out[q] = 0.0f; }
+                unsigned lmask = 0u;
+                if (emit && a.prefilter) {
+                    lmask = light_root_mask(s, out_o, out_d);
+                    if (lmask == 0u) { cand = false; a.lsum_out[q] = 0.0f; }
+                    if (a.prefilter < 2) lmask = 0u;
+                }
                 const unsigned cmask = __ballot_sync(0xffffffffu, cand);
                 if (cmask) {
                     const int cl = __ffs(cmask) - 1;
                     uint32_t cbase = 0;
                     if (lane == cl) cbase = atomicAdd(a.lq_count, (uint32_t)__popc(cmask));
                     cbase = __shfl_sync(0xffffffffu, cbase, cl);
-                    if (cand) a.lq[cbase + __popc(cmask & ((1u << lane) - 1u))] = q;
+                    if (cand) a.lq[cbase + __popc(cmask & ((1u << lane) - 1u))] = q | (lmask << LQ_MASK_SHIFT);
                 }
             }
         }

@@ -44,7 +44,7 @@ struct ort_ctx {
     // re-uploading a scene of the same shape performs no cudaMalloc / cudaFree (a cudaFree was
     // measured at 15-600 ms on B200 boxes: it synchronises the device and unmaps).
     struct DevBuf { void* p = nullptr; size_t cap = 0, used = 0; };
-    enum { SB_NODES, SB_TRIS, SB_LLIGHT, SB_MATS, SB_TSHADE, SB_TUV, SB_TTAN, SB_TEXS, SB_COUNT };
+    enum { SB_NODES, SB_TRIS, SB_MATS, SB_TSHADE, SB_TUV, SB_TTAN, SB_TEXS, SB_COUNT };
     DevBuf sbuf[SB_COUNT];
     struct TexSlot { cudaArray_t arr = nullptr; cudaTextureObject_t obj = 0; size_t w = 0, h = 0; bool in_use = false; };
     std::vector<TexSlot> tex_pool;
@@ -111,7 +111,8 @@ struct ort_ctx {
     int tiled = 2;           // 0 = primary rays in pixel order, 1 = 8x4 pixel tiles, 2 = tile_w x tile_h pixels x tile_s samples per warp
     int tile_w = 2, tile_h = 2, tile_s = 8;
     int bin_octants = 1;     // 0: plain per-warp queue compaction (no direction-octant binning)
-    int light_prefilter = 1; // 0: send every continuation ray through the light pass
+    int light_prefilter = 2; // 0: send every continuation ray through the light pass; 1: only rays that enter a child
+                             // box of the light root; 2: those, starting the light pass AT the entered children
     int refill = ORT_REFILL_THRESHOLD; // dynamic-fetch threshold of the closest-hit pass
     int refill_light = ORT_REFILL_LIGHT; // ... of the light pass
     int inner_min = ORT_INNER_MIN;     // inner-loop early-exit threshold
@@ -435,9 +436,9 @@ int ensure_pinned(ort_ctx* ctx, size_t bytes) {
 // mode 0: closest hit, 1: light-pdf sum
 void launch_trace(ort_ctx* ctx, ort_ctx::PathSet& P, cudaStream_t st, const float4* qo, const float4* qd,
                   const uint32_t* n_ptr, uint32_t* work_ctr, int mode, float* lsum = nullptr,
-                  const uint32_t* index = nullptr) {
+                  const uint32_t* index = nullptr, int index_packed = 0) {
     TraceArgs a;
-    a.qo = qo; a.qd = qd; a.n_ptr = n_ptr; a.work_ctr = work_ctr; a.index = index;
+    a.qo = qo; a.qd = qd; a.n_ptr = n_ptr; a.work_ctr = work_ctr; a.index = index; a.index_packed = index_packed;
     a.hits = P.hits; a.lsum = lsum ? lsum : P.lsum;
     a.refill_threshold = mode == 0 ? ctx->refill : ctx->refill_light; a.inner_min = ctx->inner_min;
     if (mode == 0) k_trace<false><<<ctx->trace_grid[0], TRACE_THREADS, 0, st>>>(ctx->sd, a);
@@ -485,7 +486,9 @@ int launch_wave(ort_ctx* ctx, ort_ctx::PathSet& P, cudaStream_t st, cudaEvent_t 
     uint32_t* used = P.counters + 3 * (D + 2);
     uint32_t* lcount = P.counters + 4 * (D + 2);
     const bool lights = ctx->sd.n_lights > 0;
-    const int prefilter = ctx->light_prefilter ? 1 : 0;
+    // light-queue entries carry the root-children mask in their top bits when the wave's positions fit below them
+    const int packed = (uint64_t)p.n_batch_samples * p.npix <= ((uint64_t)1 << LQ_MASK_SHIFT) ? 1 : 0;
+    const int prefilter = ctx->light_prefilter >= 2 ? 1 + packed : (ctx->light_prefilter ? 1 : 0);
     {
         Prof pr(ctx, &ctx->ms_other);
         CK(cudaMemsetAsync(P.counters, 0, sizeof(uint32_t) * 5 * (size_t)(D + 2), st));
@@ -506,7 +509,7 @@ int launch_wave(ort_ctx* ctx, ort_ctx::PathSet& P, cudaStream_t st, cudaEvent_t 
         if (need_light) {
             // only the rays k_shade queued as light candidates (the others already have lsum = 0)
             Prof pr(ctx, &ctx->ms_light);
-            launch_trace(ctx, P, st, P.qo[in], P.qd[in], lcount + k, wlight + k, 1, lsum_in, P.lq);
+            launch_trace(ctx, P, st, P.qo[in], P.qd[in], lcount + k, wlight + k, 1, lsum_in, P.lq, prefilter == 2);
         }
         {
             Prof pr(ctx, &ctx->ms_shade);
@@ -919,12 +922,7 @@ int upload_scene_impl(ort_ctx* ctx, const ort_scene* sc, SharedWide* shared) {
             return 1;
         if (bad_material.load()) { cudaStreamSynchronize(ctx->stream); return fail(ctx, "triangle material_index out of range"); }
         if (staged_upload(ctx, (char*)d_isect + nt * sizeof(TriIsect), nlt, sizeof(TriIsect), 4096,
-                          [&](size_t f, size_t c, void* o) { make_isect_records(sc->light_triangles + f, (int64_t)c, (TriIsect*)o); }))
-            return 1;
-        if (scene_buffer(ctx, ort_ctx::SB_LLIGHT, nlt * sizeof(TriLight), &d)) return 1;
-        sd.llight = (const float4*)d;
-        if (staged_upload(ctx, d, nlt, sizeof(TriLight), 4096,
-                          [&](size_t f, size_t c, void* o) { make_light_records(sc->light_triangles + f, (int64_t)c, (TriLight*)o); }))
+                          [&](size_t f, size_t c, void* o) { make_isect_records(sc->light_triangles + f, (int64_t)c, (TriIsect*)o, true); }))
             return 1;
     }
     pt.mark("triangle_records");

@@ -97,7 +97,7 @@ namespace ort {
 
 // Triangle records are read once per leaf visit: they bypass L1 allocation and leave the L1 to the nodes
 // (+0.7 % on C2 and C4; a prefetch of the leaf's first triangle line while the lane waits for the others to finish
-// descending was 3-5 % slower: profiles/r2_traversal_round2.md).
+// descending was 3-5 % slower: profiles/r2_zero_direction_components.md, last table).
 __device__ __forceinline__ F8 ldg8_noalloc(const void* p) {
     F8 r;
     asm("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -110,7 +110,9 @@ __device__ __forceinline__ F8 ldg8_noalloc(const void* p) {
 struct TraceArgs {
     const float4* qo;       // ray origins (xyz) + path slot (w), compacted queue order
     const float4* qd;       // ray directions
-    const uint32_t* index;  // optional: queue positions to process (light-candidate list); NULL = 0..n-1
+    const uint32_t* index;  // optional: queue positions to process (light-candidate list: position | root-children
+                            // mask << LQ_MASK_SHIFT when index_packed); NULL = 0..n-1
+    int index_packed;       // 0: index holds plain positions (waves of more than 2^28 paths)
     const uint32_t* n_ptr;  // number of rays to process (device resident)
     uint32_t* work_ctr;     // persistent-thread work counter
     float4* hits;           // out: (t, u, v, tri)                     (closest hit)
@@ -122,7 +124,7 @@ struct TraceArgs {
 // LIGHT = false: closest hit on the scene BVH (every bounce).  LIGHT = true: all-hit pdf sum on the
 // light BVH (bounces > 0, only over the light-candidate queue).
 template <bool LIGHT>
-__global__ void __launch_bounds__(TRACE_THREADS, ORT_TRACE_MIN_CTAS)
+__global__ void __launch_bounds__(TRACE_THREADS, LIGHT ? ORT_LIGHT_MIN_CTAS : ORT_TRACE_MIN_CTAS)
 k_trace(const SceneDev s, const TraceArgs a) {
 #if ORT_SMEM_STACK > 0
     __shared__ uint2 sh_stack[SMEM_STACK][TRACE_THREADS];
@@ -155,11 +157,28 @@ k_trace(const SceneDev s, const TraceArgs a) {
             if (idle) {
                 uint32_t idx = base + __popc(idle_mask & lt_mask);
                 if (idx < n) {
-                    if (a.index) idx = __ldg(a.index + idx);
+                    uint32_t rmask = 0u;
+                    if (a.index) {
+                        idx = __ldg(a.index + idx);
+                        if (a.index_packed) { rmask = idx >> LQ_MASK_SHIFT; idx &= LQ_POS_MASK; }
+                    }
                     r = make_ray(ldg4(a.qo + idx), ldg4(a.qd + idx), s.pad_scale);
                     best = inf; hu = 0.0f; hv = 0.0f; htri = -1; lsumv = 0.0f; // max_dist = +inf (raytracer.odin:435)
                     cull = inf; sp = 0; pos = idx;
                     cur = LIGHT ? s.light_root : 0;
+                    if (LIGHT && rmask != 0u) {
+                        // k_shade has already tested the root's child boxes for this ray (light_root_mask):
+                        // start at the children it enters (any order: the sum needs none)
+                        const int4 rc = __ldg(reinterpret_cast<const int4*>(s.nodes + (size_t)s.light_root * 8 + 6));
+                        cur = WIDE_EMPTY;
+#define ORT_START(BIT, C)                                                  \
+    if (rmask & BIT) {                                                     \
+        if (cur != WIDE_EMPTY) ORT_PUSH(cur, 0.0f)                         \
+        cur = C;                                                           \
+    }
+                        ORT_START(8u, rc.w) ORT_START(4u, rc.z) ORT_START(2u, rc.y) ORT_START(1u, rc.x)
+#undef ORT_START
+                    }
                 }
             }
             exhausted = base + (uint32_t)cnt >= n;
@@ -236,19 +255,24 @@ k_trace(const SceneDev s, const TraceArgs a) {
                         }
                     } else {
                         // surface_sampling_pdf_trigs_sum (shading.odin:52-60): the reference's intersect
-                        // returns t = -1 when (u,v) is outside, then `!(t >= 0)` skips
+                        // returns t = -1 when (u,v) is outside, then `!(t >= 0)` skips.  ng and 2 / |u x v| of a
+                        // light triangle sit in the last 16 bytes of its record (TriIsect::light).
+#define ORT_LIGHT_TEST(TA, TB, TCL)                                                                   \
+    {                                                                                                 \
+        float id, bx, by, bz, t, a00, a10, u, v;                                                      \
+        tri_det_t(r, TA, TB, TCL.lo, id, bx, by, bz, t, a00, a10);                                    \
+        if (t >= 0.0f && tri_uv(r, TA, TB, TCL.lo, id, bx, by, bz, a00, a10, u, v)) {                 \
+            const float4 L = TCL.hi;                                                                  \
+            const float weight = (t * t) / fabsf(L.x * r.dx + L.y * r.dy + L.z * r.dz);               \
+            lsumv += L.w * weight;                                                                    \
+        }                                                                                             \
+    }
                         for (uint32_t i = 0; i < cnt; i++) {
                             const float4* tp = s.tris + (size_t)(first + i) * 4;
-                            const F8 tab = ORT_LDG8_TRI(tp);
-                            const float4 ta = tab.lo, tb = tab.hi, tc = ldg4(tp + 2);
-                            float id, bx, by, bz, t, a00, a10, u, v;
-                            tri_det_t(r, ta, tb, tc, id, bx, by, bz, t, a00, a10);
-                            if (t >= 0.0f && tri_uv(r, ta, tb, tc, id, bx, by, bz, a00, a10, u, v)) {
-                                const float4 L = ldg4(s.llight + (first + i - s.light_tri_base));
-                                const float weight = (t * t) / fabsf(L.x * r.dx + L.y * r.dy + L.z * r.dz);
-                                lsumv += L.w * weight;
-                            }
+                            const F8 tab = ORT_LDG8_TRI(tp), tcl = ORT_LDG8_TRI(tp + 2);
+                            ORT_LIGHT_TEST(tab.lo, tab.hi, tcl)
                         }
+#undef ORT_LIGHT_TEST
                     }
                     cur = WIDE_EMPTY;
                     while (sp > 0) {

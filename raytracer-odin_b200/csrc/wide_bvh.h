@@ -30,22 +30,25 @@ struct alignas(16) WideNode {
 static_assert(sizeof(WideNode) == 128, "WideNode must be one cache line");
 constexpr int32_t WIDE_EMPTY = (int32_t)0x80000000;
 
+// Light-candidate queue entry (k_shade -> k_trace<light>): the ray's position in the ray queue in the low 28 bits,
+// the mask of the light root's children whose boxes the ray enters in the top four (0 = start at the root).
+// A wave therefore holds at most 2^28 paths (the default is 2^25).
+constexpr uint32_t LQ_MASK_SHIFT = 28u;
+constexpr uint32_t LQ_POS_MASK = (1u << LQ_MASK_SHIFT) - 1u;
+
 // Traversal record, 64 bytes = 2 x LDG.256: p, u, v and the ray-independent third row of the
 // adjugate of [u | v | -d] (raytracer.odin:138-142): c = (uy*vz - uz*vy, -(ux*vz - uz*vx),
-// ux*vy - uy*vx), each product and difference individually rounded.
+// ux*vy - uy*vx), each product and difference individually rounded.  The last 16 bytes are used by the
+// records of the LIGHT triangles only (all-hit pdf sum, shading.odin:52-60): ng and 2 / length(cross(u, v)) arrive
+// with the second half of the record instead of through a dependent load after a hit (that load was 10 % of the
+// light pass's stall samples at 2 active lanes: profiles/r2s_light_pass.md).
 struct alignas(32) TriIsect {
     float p[3], ux;
     float uy, uz, vx, vy;
     float vz, c0, c1, c2;
-    float pad[4];
+    float light[4]; // ng.xyz, 2 / |u x v|   (zero for scene triangles)
 };
 static_assert(sizeof(TriIsect) == 64, "TriIsect");
-
-// Extra record for light triangles (all-hit pdf sum, shading.odin:52-60): ng and
-// k = 2 / length(cross(u, v)).
-struct alignas(16) TriLight {
-    float ng[3], k;
-};
 
 // Shading records.
 struct alignas(16) TriShade { // 64 bytes
@@ -80,8 +83,7 @@ bool build_wide_bvh(const ort_bvh_node* bvh, int64_t n_nodes, int64_t n_tris, Wi
 // the reference silently drops pushes; this library never does (ort_stats.reference_stack_need).
 int64_t reference_stack_need(const ort_bvh_node* bvh, int64_t n_nodes);
 
-void make_isect_records(const ort_triangle* tris, int64_t n, TriIsect* out);
-void make_light_records(const ort_triangle* tris, int64_t n, TriLight* out);
+void make_isect_records(const ort_triangle* tris, int64_t n, TriIsect* out, bool light = false);
 
 // pixel_to_ray_dir (raytracer.odin:529-538), row-major m[r*4+c].
 void make_pixel_to_ray_dir(const ort_camera& cam, uint32_t w, uint32_t h, float m[16]);
