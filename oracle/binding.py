@@ -25,18 +25,19 @@ _libs = {}
 
 
 def build(force=False):
-    if force or not all(os.path.exists(os.path.join(HERE, n)) for n in ("liboracle.so", "liboracle_native.so")):
+    if force or not all(os.path.exists(os.path.join(HERE, n)) for n in ("liboracle.so", "liboracle_native.so",
+                                                                         "liboracle_alt.so")):
         subprocess.check_call(["make", "-C", HERE] + (["-B"] if force else []), stdout=subprocess.DEVNULL)
 
 
 def load(native=False):
     """native=False: -O2 build used as the CHECKER; native=True: -O3 -march=native build used as
     the TIMED CPU baseline (the reference's `brrr` flags analogue, justfile:37-41).  Both are
-    -ffp-contract=off."""
-    key = bool(native)
+    -ffp-contract=off.  native="alt": the ORC_VARIANTS build of the sensitivity study (orc_set_variant)."""
+    key = native if native == "alt" else bool(native)
     if key in _libs:
         return _libs[key]
-    name = "liboracle_native.so" if native else "liboracle.so"
+    name = "liboracle_alt.so" if native == "alt" else ("liboracle_native.so" if native else "liboracle.so")
     path = os.path.join(HERE, name)
     if not os.path.exists(path):
         build()
@@ -68,6 +69,8 @@ def load(native=False):
         "orc_get_rgb_image": (None, [vp, u32, u32, vp]),
         "orc_hardware_threads": (i32, []),
     }
+    if key == "alt":
+        sig["orc_set_variant"] = (None, [i32])
     for n, (res, args) in sig.items():
         fn = getattr(lib, n)
         fn.restype, fn.argtypes = res, args
@@ -80,11 +83,11 @@ def _fa(a):
     return a, a.ctypes.data_as(C.POINTER(C.c_float))
 
 
-def bvh_build(tris: np.ndarray) -> np.ndarray:
+def bvh_build(tris: np.ndarray, native=False) -> np.ndarray:
     """bvh_build (raytracer.odin:227-342) — sorts `tris` in place, returns the node array."""
     from raytracer_odin_b200 import cabi
 
-    lib = load()
+    lib = load(native)
     n = len(tris)
     cap = max(2 * n, 1)
     nodes = np.zeros(cap, cabi.NODE_DTYPE)

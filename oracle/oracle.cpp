@@ -171,11 +171,51 @@ struct GeomHit {
     bool inside;
     float t, u, v;
 };
+#ifdef ORC_VARIANTS
+// SENSITIVITY STUDY ONLY (liboracle_alt.so, tests/test_oracle_sensitivity.py): alternative definitions of the
+// operations whose order lives in Odin's `core:` / compiler, to MEASURE how much of the parity claim depends on the
+// choice made above.  Never compiled into liboracle.so / liboracle_native.so.
+//   bit 0  inverse = adjugate / det            (nine divisions instead of adjugate * (1/det))
+//   bit 1  det expanded along the first column (m00*a00 + m10*a01 + m20*a02)
+//   bit 2  every a*b - c*d contracted to fma(a, b, -(c*d))   (a compiler that contracts)
+//   bit 3  matrix * vector with fused multiply-adds: fma(i2, b2, fma(i1, b1, i0*b0))   (llvm.fmuladd lowering)
+//   bit 4  bvh_build's sort breaks ties in REVERSE input order (an unstable sort's other extreme)
+int g_variant = 0;
+inline float pd(float a, float b, float c, float d) { // a*b - c*d
+    return (g_variant & 4) ? std::fma(a, b, -(c * d)) : a * b - c * d;
+}
+inline float mv(float i0, float i1, float i2, V3 b) {
+    return (g_variant & 8) ? std::fma(i2, b.z, std::fma(i1, b.y, i0 * b.x)) : i0 * b.x + i1 * b.y + i2 * b.z;
+}
+#endif
 inline GeomHit intersect_ray_triangle(const Ray& ray, const ort_triangle& tr) {
     V3 b = ray.o - v3(tr.p);
     float m00 = tr.u[0], m10 = tr.u[1], m20 = tr.u[2];
     float m01 = tr.v[0], m11 = tr.v[1], m21 = tr.v[2];
     float m02 = -ray.d.x, m12 = -ray.d.y, m22 = -ray.d.z;
+#ifdef ORC_VARIANTS
+    if (g_variant & 15) {
+        float a00 = +pd(m11, m22, m21, m12), a01 = -pd(m01, m22, m21, m02), a02 = +pd(m01, m12, m11, m02);
+        float a10 = -pd(m10, m22, m20, m12), a11 = +pd(m00, m22, m20, m02), a12 = -pd(m00, m12, m10, m02);
+        float a20 = +pd(m10, m21, m20, m11), a21 = -pd(m00, m21, m20, m01), a22 = +pd(m00, m11, m10, m01);
+        float det;
+        if (g_variant & 2) det = m00 * a00 + m10 * a01 + m20 * a02;
+        else det = m00 * pd(m11, m22, m12, m21) + (-m01) * pd(m10, m22, m12, m20) + m02 * pd(m10, m21, m11, m20);
+        float u, v, t;
+        if (g_variant & 1) {
+            u = mv(a00 / det, a01 / det, a02 / det, b);
+            v = mv(a10 / det, a11 / det, a12 / det, b);
+            t = mv(a20 / det, a21 / det, a22 / det, b);
+        } else {
+            float id = 1.0f / det;
+            u = mv(a00 * id, a01 * id, a02 * id, b);
+            v = mv(a10 * id, a11 * id, a12 * id, b);
+            t = mv(a20 * id, a21 * id, a22 * id, b);
+        }
+        if (u < 0 || v < 0 || u + v > 1) return {false, -1.0f, 0, 0};
+        return {dot(v3(tr.ng), ray.d) > 0, t, u, v};
+    }
+#endif
     float a00 = +(m11 * m22 - m21 * m12), a01 = -(m01 * m22 - m21 * m02), a02 = +(m01 * m12 - m11 * m02);
     float a10 = -(m10 * m22 - m20 * m12), a11 = +(m00 * m22 - m20 * m02), a12 = -(m00 * m12 - m10 * m02);
     float a20 = +(m10 * m21 - m20 * m11), a21 = -(m00 * m21 - m20 * m01), a22 = +(m00 * m11 - m10 * m01);
@@ -212,6 +252,14 @@ struct Builder {
     // try_axis (:276-304)
     void try_axis(int axis, int64_t b, int64_t n, float* best_sah_out, int64_t* best_index_out) {
         Item* it = items.data() + b;
+#ifdef ORC_VARIANTS
+        if (g_variant & 16) {
+            std::reverse(it, it + n); // ties now come out in reverse order of the (previous) sequence
+            std::stable_sort(it, it + n, [axis](const Item& l, const Item& r) {
+                return axis_of(l.box.lo, axis) < axis_of(r.box.lo, axis);
+            });
+        } else
+#endif
         std::stable_sort(it, it + n, [axis](const Item& l, const Item& r) {
             return axis_of(l.box.lo, axis) < axis_of(r.box.lo, axis);
         });
@@ -1027,5 +1075,8 @@ void orc_get_rgb_image(const ort_sample_stats* px, uint32_t w, uint32_t h, uint8
 }
 
 int orc_hardware_threads(void) { return (int)std::thread::hardware_concurrency(); }
+#ifdef ORC_VARIANTS
+void orc_set_variant(int bits) { g_variant = bits; }
+#endif
 
 } // extern "C"
