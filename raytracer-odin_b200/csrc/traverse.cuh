@@ -58,11 +58,18 @@ namespace ort {
 // plane distance of the x axis is +inf and the far one -inf, so the slab test can never pass and no
 // separate validity compare is needed.
 
-// Stack entry = (node reference, entry distance bits): one 64-bit access per push / pop.
-#if ORT_SMEM_STACK > 0
+// Stack entry = (node reference, entry distance bits): one 64-bit access per push / pop.  The all-hit light pass
+// never culls by distance, so its entries are the 32-bit node reference alone (half the shared memory per CTA).
+template <bool NODE_ONLY> struct StackEntry { using T = uint2; };
+template <> struct StackEntry<true> { using T = uint32_t; };
+#ifndef ORT_LIGHT_STACK32
+#define ORT_LIGHT_STACK32 0
+#endif
 #define ORT_PUSH(NODE, DIST)                                                                          \
     {                                                                                                 \
-        const uint2 e_ = make_uint2((uint32_t)(NODE), __float_as_uint(DIST));                         \
+        E e_;                                                                                         \
+        if constexpr (sizeof(E) == 4) e_ = (uint32_t)(NODE);                                          \
+        else e_ = make_uint2((uint32_t)(NODE), __float_as_uint(DIST));                                \
         if (sp < SMEM_STACK) sh_stack[sp][threadIdx.x] = e_;                                          \
         else l_stack[sp - SMEM_STACK] = e_;                                                           \
         sp++;                                                                                         \
@@ -70,22 +77,10 @@ namespace ort {
 #define ORT_POP(NODE, DIST)                                                                           \
     {                                                                                                 \
         sp--;                                                                                         \
-        const uint2 e_ = sp < SMEM_STACK ? sh_stack[sp][threadIdx.x] : l_stack[sp - SMEM_STACK];      \
-        NODE = (int)e_.x; DIST = __uint_as_float(e_.y);                                               \
+        const E e_ = sp < SMEM_STACK ? sh_stack[sp][threadIdx.x] : l_stack[sp - SMEM_STACK];          \
+        if constexpr (sizeof(E) == 4) { NODE = (int)e_; DIST = 0.0f; }                                \
+        else { NODE = (int)e_.x; DIST = __uint_as_float(e_.y); }                                      \
     }
-#else // experiment: the whole stack in thread-local memory (L1-cached), no shared memory, no split
-#define ORT_PUSH(NODE, DIST)                                                                          \
-    {                                                                                                 \
-        l_stack[sp] = make_uint2((uint32_t)(NODE), __float_as_uint(DIST));                            \
-        sp++;                                                                                         \
-    }
-#define ORT_POP(NODE, DIST)                                                                           \
-    {                                                                                                 \
-        sp--;                                                                                         \
-        const uint2 e_ = l_stack[sp];                                                                 \
-        NODE = (int)e_.x; DIST = __uint_as_float(e_.y);                                               \
-    }
-#endif
 #define ORT_CSWAP(da, ca, db, cb)               \
     {                                           \
         const bool sw_ = db < da;               \
@@ -126,10 +121,9 @@ struct TraceArgs {
 template <bool LIGHT>
 __global__ void __launch_bounds__(TRACE_THREADS, LIGHT ? ORT_LIGHT_MIN_CTAS : ORT_TRACE_MIN_CTAS)
 k_trace(const SceneDev s, const TraceArgs a) {
-#if ORT_SMEM_STACK > 0
-    __shared__ uint2 sh_stack[SMEM_STACK][TRACE_THREADS];
-#endif
-    uint2 l_stack[LOCAL_STACK];
+    using E = typename StackEntry<LIGHT && ORT_LIGHT_STACK32>::T;
+    __shared__ E sh_stack[SMEM_STACK][TRACE_THREADS];
+    E l_stack[LOCAL_STACK];
 
     const uint32_t n = *a.n_ptr;
     const int lane = threadIdx.x & 31;
