@@ -63,7 +63,7 @@ namespace ort {
 template <bool NODE_ONLY> struct StackEntry { using T = uint2; };
 template <> struct StackEntry<true> { using T = uint32_t; };
 #ifndef ORT_LIGHT_STACK32
-#define ORT_LIGHT_STACK32 0
+#define ORT_LIGHT_STACK32 1
 #endif
 #define ORT_PUSH(NODE, DIST)                                                                          \
     {                                                                                                 \
